@@ -1,0 +1,77 @@
+"""ORACLE (test infrastructure only) - the whole pairwise-registration hot path on
+the CPU, stage by stage, following DeepGlobalRegistration.register()
+(core/deep_global_registration.py:238-324) up to and including the SE(3)
+refinement; the open3d ICP / RANSAC steps (:302-322) are outside the built path
+and excluded on both sides.
+
+Each stage returns its tensors so that GPU parity tests can tap in anywhere and
+feed the oracle's outputs of stage k into the CUDA stage k+1 (stage-isolated
+parity), see tests/test_gpu_pipeline.py.
+"""
+import numpy as np
+import torch
+
+from . import sparse_ops as so
+from .registration import feature_knn, inlier_weights, se3_refine
+from .resunet import resunet_forward
+
+
+def preprocess(xyz, voxel_size):
+  """core/deep_global_registration.py:134-161 -> (xyz fp32 [N,3], coords int32
+  [N,4] with batch column 0, sel)."""
+  coords, sel = so.quantize_first(xyz, voxel_size)
+  return xyz[sel].astype(np.float32), so.batched_coordinates([coords]), sel
+
+
+def fcgf(state, coords):
+  cfg = state['config']
+  feats = torch.ones(len(coords), 1)
+  return resunet_forward(state['state_dict'], coords, feats, cfg['feat_conv1_kernel_size'],
+                         cfg['normalize_feature'])
+
+
+def inlier_coords(coords0, coords1, idx1):
+  """:261-262  cat(coords0[idx0], coords1[idx1, 1:]) with idx0 = arange."""
+  return np.concatenate([coords0, coords1[idx1, 1:]], 1).astype(np.int32)
+
+
+def inlier_features(feat_type, xyz0, xyz1, idx1):
+  """:185-208"""
+  if feat_type == 'ones':
+    return torch.ones(len(idx1), 1)
+  if feat_type == 'coords':
+    return torch.cat([torch.cos(torch.from_numpy(xyz0)), torch.cos(torch.from_numpy(xyz1[idx1]))], 1)
+  raise ValueError(feat_type)
+
+
+def inlier_logits(state, coords6, feats):
+  cfg = state['config']
+  return resunet_forward(state['state_dict_inlier'], coords6, feats, cfg['inlier_conv1_kernel_size'],
+                         False)
+
+
+def register(state, xyz0, xyz1, clip_weight_thresh=0.05):
+  """Returns (T 4x4 float64, taps dict).  T is identity when the weight-sum gate
+  (:276-281) sends the pair to the safeguard branch, which is not part of the
+  built path; taps['branch'] says which branch was taken."""
+  cfg = state['config']
+  vs = cfg['voxel_size']
+  p0, c0, sel0 = preprocess(xyz0, vs)
+  p1, c1, sel1 = preprocess(xyz1, vs)
+  f0, f1 = fcgf(state, c0), fcgf(state, c1)
+  idx1 = feature_knn(f0, f1, cfg['nn_max_n']).numpy()
+  c6 = inlier_coords(c0, c1, idx1)
+  logit = inlier_logits(state, c6, inlier_features(cfg['inlier_feature_type'], p0, p1, idx1))
+  w = inlier_weights(logit, clip_weight_thresh)
+  wsum = float(w.sum())
+  taps = dict(xyz0=p0, xyz1=p1, coords0=c0, coords1=c1, sel0=sel0, sel1=sel1, feat0=f0, feat1=f1,
+              idx1=idx1, coords6=c6, logit=logit, weights=w, wsum=wsum)
+  T = np.eye(4)
+  if wsum >= max(200, len(w) * 0.05):
+    R, t, info = se3_refine(p0, p1[idx1], w, 2 * vs)
+    T[:3, :3] = R.numpy()
+    T[:3, 3] = t.numpy().reshape(3)
+    taps.update(branch='procrustes', refine=info)
+  else:
+    taps.update(branch='safeguard')
+  return T, taps
