@@ -1,0 +1,341 @@
+"""ctypes binding of libdgr_b200.so (include/dgr_b200.h).
+
+torch is used here for device memory and the current CUDA stream only; every
+computation happens inside the library.  There is no CPU fallback: importing this
+module without a built library, or calling into it without an sm_100 device,
+raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdgr_b200.so')
+
+MAX_COLS = 8
+TILE_ROWS = 128
+
+
+class KeySpec(C.Structure):
+  _fields_ = [('ncols', C.c_int32), ('overflow', C.c_int32), ('lo', C.c_int32 * MAX_COLS),
+              ('shift', C.c_int32 * MAX_COLS), ('bits', C.c_int32 * MAX_COLS)]
+
+
+KEYSPEC_INTS = C.sizeof(KeySpec) // 4
+
+_p, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+# name -> argtypes; every function returns int32 status unless listed in _RESTYPES
+SIGNATURES = {
+    'dgr_version': [],
+    'dgr_last_error': [],
+    'dgr_device_check': [_i32],
+    'dgr_quantize_points': [_p, _i32, _i64, _f64, _i32, _p, _p, _p],
+    'dgr_coords_minmax': [_p, _i64, _i32, _p, _p],
+    'dgr_keyspec_build': [_p, _i32, _i32, _p, _p],
+    'dgr_hash_clear': [_p, _p, _i64, _p],
+    'dgr_unique_first': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
+    'dgr_scan_ws_elems': [_i64],
+    'dgr_hash_find': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _p],
+    'dgr_gather_rows_i32': [_p, _p, _i64, _i32, _p, _p],
+    'dgr_stride_coords': [_p, _i64, _i32, _i32, _p, _p],
+    'dgr_kernel_map_table': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _i32, _p, _p],
+    'dgr_kmap_ws_elems': [_i32, _i64],
+    'dgr_kernel_map_count': [_p, _i32, _i64, _p, _p, _p],
+    'dgr_kernel_map_fill': [_p, _i32, _i64, _p, _p, _p, _p],
+    'dgr_kernel_map_tiles': [_p, _i32, _i32, _i32, _p, _p, _p],
+    'dgr_spconv_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
+    'dgr_spconv_table_fwd': [_p, _i32, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p],
+    'dgr_linear_fwd': [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _i32, _i32, _p, _p],
+    'dgr_affine_act': [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p],
+    'dgr_cat2': [_p, _i32, _p, _i32, _i64, _p, _p],
+    'dgr_l2_normalize': [_p, _i64, _i32, _p, _p],
+    'dgr_knn_top1': [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p],
+    'dgr_inlier_coords': [_p, _p, _p, _i64, _p, _p],
+    'dgr_sigmoid_clip_sum': [_p, _i64, _f32, _p, _p, _p],
+    'dgr_se3_register': [_p, _p, _p, _p, _i64, _f32, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p],
+}
+_RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
+
+_lib = None
+
+
+class DgrError(RuntimeError):
+  pass
+
+
+def lib():
+  """Load the shared library (once).  Fails loudly when it has not been built."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise DgrError(f'{LIB_PATH} is missing: run `python -m deepglobalregistration_b200.build` '
+                     '(there is no CPU fallback)')
+    l = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+      fn = getattr(l, name)
+      fn.argtypes = args
+      fn.restype = _RESTYPES.get(name, _i32)
+    _lib = l
+  return _lib
+
+
+def _check(status, name):
+  if status != 0:
+    raise DgrError(f'{name} failed ({status}): {lib().dgr_last_error().decode()}')
+
+
+def call(name, *args):
+  _check(getattr(lib(), name)(*args), name)
+
+
+_checked_devices = set()
+
+
+def require_device(device):
+  device = torch.device(device)
+  if device.type != 'cuda':
+    raise DgrError(f'libdgr_b200 computes on CUDA (sm_100a) only, got device {device}; there is no '
+                   'CPU fallback')
+  idx = device.index if device.index is not None else torch.cuda.current_device()
+  if idx not in _checked_devices:
+    _check(lib().dgr_device_check(idx), 'dgr_device_check')
+    _checked_devices.add(idx)
+  return torch.device('cuda', idx)
+
+
+def ptr(t):
+  return 0 if t is None else t.data_ptr()
+
+
+def stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+  if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+    raise DgrError(f'{name}: expected contiguous CUDA {dtype}, got {t.dtype} on {t.device} '
+                   f'(contiguous={t.is_contiguous()})')
+  return t
+
+
+def next_pow2(n):
+  p = 1
+  while p < n:
+    p <<= 1
+  return p
+
+
+# --------------------------------------------------------------------------- #
+# thin typed wrappers (allocate outputs / workspaces with torch, call the ABI)
+# --------------------------------------------------------------------------- #
+class HashTable:
+  __slots__ = ('keys', 'vals', 'cap')
+
+  def __init__(self, n, device):
+    self.cap = max(1024, next_pow2(2 * max(int(n), 1)))
+    self.keys = torch.empty(self.cap, dtype=torch.int64, device=device)
+    self.vals = torch.empty(self.cap, dtype=torch.int32, device=device)
+    call('dgr_hash_clear', ptr(self.keys), ptr(self.vals), self.cap, stream())
+
+
+def quantize_points(xyz, voxel, batch=0):
+  """xyz CUDA float64/float32 [n,3] -> (coords int32 [n,4], minmax int32 [8])."""
+  assert xyz.is_cuda and xyz.is_contiguous() and xyz.shape[1] == 3
+  is64 = {torch.float64: 1, torch.float32: 0}[xyz.dtype]
+  n = xyz.shape[0]
+  coords = torch.empty(n, 4, dtype=torch.int32, device=xyz.device)
+  minmax = torch.empty(8, dtype=torch.int32, device=xyz.device)
+  call('dgr_quantize_points', ptr(xyz), is64, n, float(voxel), int(batch), ptr(coords), ptr(minmax),
+       stream())
+  return coords, minmax
+
+
+def coords_minmax(coords):
+  _chk(coords, torch.int32, 'coords')
+  minmax = torch.empty(2 * coords.shape[1], dtype=torch.int32, device=coords.device)
+  call('dgr_coords_minmax', ptr(coords), coords.shape[0], coords.shape[1], ptr(minmax), stream())
+  return minmax
+
+
+def keyspec_build(minmax, ncols, margin=32):
+  spec = torch.empty(KEYSPEC_INTS, dtype=torch.int32, device=minmax.device)
+  call('dgr_keyspec_build', ptr(minmax), ncols, margin, ptr(spec), stream())
+  return spec
+
+
+def unique_first(coords, spec):
+  """-> (table, sel int32 [n] (first m valid), inverse int32 [n], n_unique device int32 [1])."""
+  _chk(coords, torch.int32, 'coords')
+  n, ncols = coords.shape
+  dev = coords.device
+  table = HashTable(n, dev)
+  sel = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+  inverse = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+  cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+  slot = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+  rank = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+  scan = torch.empty(lib().dgr_scan_ws_elems(n), dtype=torch.int32, device=dev)
+  call('dgr_unique_first', ptr(coords), n, ncols, ptr(spec), ptr(table.keys), ptr(table.vals), table.cap,
+       ptr(sel), ptr(inverse), ptr(cnt), ptr(slot), ptr(rank), ptr(scan), stream())
+  return table, sel, inverse, cnt
+
+
+def hash_find(coords, spec, table):
+  _chk(coords, torch.int32, 'coords')
+  rows = torch.empty(coords.shape[0], dtype=torch.int32, device=coords.device)
+  call('dgr_hash_find', ptr(coords), coords.shape[0], coords.shape[1], ptr(spec), ptr(table.keys),
+       ptr(table.vals), table.cap, ptr(rows), stream())
+  return rows
+
+
+def gather_rows_i32(src, idx, n):
+  out = torch.empty(n, src.shape[1], dtype=torch.int32, device=src.device)
+  call('dgr_gather_rows_i32', ptr(src), ptr(idx), n, src.shape[1], ptr(out), stream())
+  return out
+
+
+def stride_coords(coords, out_stride):
+  out = torch.empty_like(coords)
+  call('dgr_stride_coords', ptr(coords), coords.shape[0], coords.shape[1], out_stride, ptr(out), stream())
+  return out
+
+
+class KernelMap:
+  """Neighbour table + (kappa, j)-sorted pair lists + the gather-GEMM-scatter work list."""
+  __slots__ = ('K', 'n_in', 'n_out', 'nbr', 'in_idx', 'out_idx', 'kofs', 'kofs_host', 'n_pairs',
+               'tile_k', 'tile_start', 'n_tiles')
+
+  def transposed(self):
+    t = KernelMap()
+    for k in self.__slots__:
+      setattr(t, k, getattr(self, k))
+    t.in_idx, t.out_idx = self.out_idx, self.in_idx
+    t.n_in, t.n_out = self.n_out, self.n_in
+    t.nbr = None
+    return t
+
+
+def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
+  """offsets: CUDA int32 [K, D] (scaled by the input tensor stride)."""
+  _chk(out_coords, torch.int32, 'out_coords')
+  _chk(offsets, torch.int32, 'offsets')
+  dev = out_coords.device
+  n_out, ncols = out_coords.shape
+  K = offsets.shape[0]
+  km = KernelMap()
+  km.K, km.n_in, km.n_out = K, n_in, n_out
+  nbr = torch.empty(K, max(n_out, 1), dtype=torch.int32, device=dev)
+  call('dgr_kernel_map_table', ptr(out_coords), n_out, ncols, ptr(spec), ptr(in_table.keys),
+       ptr(in_table.vals), in_table.cap, ptr(offsets), K, ptr(nbr), stream())
+  ws = torch.empty(lib().dgr_kmap_ws_elems(K, n_out), dtype=torch.int32, device=dev)
+  kofs = torch.empty(K + 1, dtype=torch.int32, device=dev)
+  call('dgr_kernel_map_count', ptr(nbr), K, n_out, ptr(ws), ptr(kofs), stream())
+  kofs_host = kofs.cpu().numpy()          # the one host read of this map: P and the tile count
+  P = int(kofs_host[K])
+  counts = kofs_host[1:] - kofs_host[:-1]
+  n_tiles = int(((counts + TILE_ROWS - 1) // TILE_ROWS).sum())
+  km.in_idx = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+  km.out_idx = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+  if n_out > 0:
+    call('dgr_kernel_map_fill', ptr(nbr), K, n_out, ptr(ws), ptr(km.in_idx), ptr(km.out_idx), stream())
+  km.tile_k = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
+  km.tile_start = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
+  call('dgr_kernel_map_tiles', ptr(kofs), K, TILE_ROWS, n_tiles, ptr(km.tile_k), ptr(km.tile_start), stream())
+  km.kofs, km.kofs_host, km.n_pairs, km.n_tiles = kofs, kofs_host, P, n_tiles
+  km.nbr = nbr if keep_table else None
+  return km
+
+
+def spconv_fwd(feat, weight, km, out, relu_in=False):
+  """out[km.out_idx] += feat[km.in_idx] @ weight[kappa]; `out` holds the initial value."""
+  _chk(feat, torch.float32, 'feat'); _chk(weight, torch.float32, 'weight'); _chk(out, torch.float32, 'out')
+  cin, cout = feat.shape[1], out.shape[1]
+  assert weight.numel() == km.K * cin * cout, (weight.shape, km.K, cin, cout)
+  assert feat.shape[0] == km.n_in and out.shape[0] == km.n_out, (feat.shape, out.shape, km.n_in, km.n_out)
+  call('dgr_spconv_fwd', ptr(feat), cin, ptr(weight), cout, ptr(km.in_idx), ptr(km.out_idx), ptr(km.kofs),
+       ptr(km.tile_k), ptr(km.tile_start), km.n_tiles, TILE_ROWS, int(relu_in), ptr(out), stream())
+  return out
+
+
+def spconv_table_fwd(feat, weight, km, cout, scale=None, shift=None):
+  _chk(feat, torch.float32, 'feat'); _chk(weight, torch.float32, 'weight')
+  assert km.nbr is not None
+  out = torch.empty(km.n_out, cout, dtype=torch.float32, device=feat.device)
+  call('dgr_spconv_table_fwd', ptr(feat), feat.shape[1], ptr(weight), cout, ptr(km.nbr), km.K, km.n_out,
+       ptr(scale), ptr(shift), ptr(out), stream())
+  return out
+
+
+def linear_fwd(a, weight, bias=None, b=None, relu=False, normalize=False):
+  _chk(a, torch.float32, 'a'); _chk(weight, torch.float32, 'weight')
+  n, ca = a.shape
+  cb = 0 if b is None else b.shape[1]
+  cout = weight.numel() // (ca + cb)
+  out = torch.empty(n, cout, dtype=torch.float32, device=a.device)
+  call('dgr_linear_fwd', ptr(a), ca, ptr(b), cb, n, ptr(weight), cout, ptr(bias), int(relu), int(normalize),
+       ptr(out), stream())
+  return out
+
+
+def affine_act(x, scale=None, shift=None, residual=None, relu=False, out=None):
+  _chk(x, torch.float32, 'x')
+  if out is None:
+    out = torch.empty_like(x)
+  call('dgr_affine_act', ptr(x), x.shape[0], x.shape[1], ptr(scale), ptr(shift), ptr(residual), int(relu),
+       ptr(out), stream())
+  return out
+
+
+def cat2(a, b):
+  _chk(a, torch.float32, 'a'); _chk(b, torch.float32, 'b')
+  out = torch.empty(a.shape[0], a.shape[1] + b.shape[1], dtype=torch.float32, device=a.device)
+  call('dgr_cat2', ptr(a), a.shape[1], ptr(b), b.shape[1], a.shape[0], ptr(out), stream())
+  return out
+
+
+def l2_normalize(x):
+  _chk(x, torch.float32, 'x')
+  out = torch.empty_like(x)
+  call('dgr_l2_normalize', ptr(x), x.shape[0], x.shape[1], ptr(out), stream())
+  return out
+
+
+def knn_top1(f0, f1, return_distance=False):
+  _chk(f0, torch.float32, 'f0'); _chk(f1, torch.float32, 'f1')
+  n0 = f0.shape[0]
+  ws = torch.empty(max(n0, 1), dtype=torch.int64, device=f0.device)
+  idx = torch.empty(n0, dtype=torch.int32, device=f0.device)
+  dist = torch.empty(n0, dtype=torch.float32, device=f0.device) if return_distance else None
+  call('dgr_knn_top1', ptr(f0), n0, ptr(f1), f1.shape[0], f0.shape[1], ptr(ws), ptr(idx), ptr(dist), stream())
+  return (idx, dist) if return_distance else idx
+
+
+def inlier_coords(coords0, coords1, idx1):
+  _chk(coords0, torch.int32, 'coords0'); _chk(coords1, torch.int32, 'coords1'); _chk(idx1, torch.int32, 'idx1')
+  out = torch.empty(coords0.shape[0], 7, dtype=torch.int32, device=coords0.device)
+  call('dgr_inlier_coords', ptr(coords0), ptr(coords1), ptr(idx1), coords0.shape[0], ptr(out), stream())
+  return out
+
+
+def sigmoid_clip_sum(logit, clip):
+  _chk(logit, torch.float32, 'logit')
+  w = torch.empty_like(logit)
+  wsum = torch.empty(1, dtype=torch.float64, device=logit.device)
+  call('dgr_sigmoid_clip_sum', ptr(logit), logit.numel(), float(clip), ptr(w), ptr(wsum), stream())
+  return w, wsum
+
+
+def se3_register(x, y, w, idx1=None, quantization_size=1.0, max_iter=1000, max_break_count=20,
+                 break_threshold_ratio=1e-4, lr=0.1, gamma=0.999):
+  """-> device float32 [16]: R (9), t (3), iterations, loss, break_count, n_active."""
+  _chk(x, torch.float32, 'x'); _chk(y, torch.float32, 'y'); _chk(w, torch.float32, 'w')
+  n = x.shape[0]
+  pack = torch.empty(7 * n, dtype=torch.float32, device=x.device)
+  cnt = torch.empty(4, dtype=torch.int32, device=x.device)
+  res = torch.empty(16, dtype=torch.float32, device=x.device)
+  call('dgr_se3_register', ptr(x), ptr(y), ptr(idx1), ptr(w), n, float(quantization_size), int(max_iter),
+       int(max_break_count), float(break_threshold_ratio), float(lr), float(gamma), ptr(pack), ptr(cnt),
+       ptr(res), stream())
+  return res

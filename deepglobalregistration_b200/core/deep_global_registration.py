@@ -1,0 +1,212 @@
+"""``DeepGlobalRegistration`` with the reference's constructor, attributes and methods
+(core/deep_global_registration.py:68-324), every stage on libdgr_b200.
+
+Built path: voxelise -> FCGF features -> feature kNN -> 6-D inlier network -> weights ->
+weighted Procrustes + SE(3) refinement.  The open3d stages around it (RANSAC safeguard
+:302-315 and ICP :317-322) are SURVEY.md §8f "next" rows and are not built: ``use_icp``
+defaults to False and the safeguard branch returns identity with ``last_branch`` set.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .. import _abi, shims
+from ..me import SparseTensor
+from ..me.coords import CoordinateManager, KEY_MARGIN
+from ..model import load_model
+from ..util.timer import Timer
+
+
+class DeepGlobalRegistration:
+  def __init__(self, config, device=torch.device('cuda')):
+    self.config = config
+    self.clip_weight_thresh = self.config.clip_weight_thresh
+    self.device = _abi.require_device(device)
+    self.safeguard_method = 'correspondence'
+    self.use_icp = False          # reference default True; ICP is a "next" row
+    self.verbose = getattr(config, 'verbose', True)
+    self.feat_timer = Timer()
+    self.reg_timer = Timer()
+    self.last_branch = None
+    self.last_info = {}
+
+    weights = config.weights
+    if isinstance(weights, dict):
+      state = weights               # already-loaded checkpoint (tests / benchmarks)
+    else:
+      self._log(f"=> loading checkpoint '{weights}'")
+      assert os.path.exists(weights)
+      shims.install()               # the checkpoint pickles an EasyDict config
+      state = torch.load(weights, map_location='cpu', weights_only=False)
+    network_config = state['config']
+    self.network_config = network_config
+    self.config.inlier_feature_type = network_config.inlier_feature_type
+    self.voxel_size = network_config.voxel_size
+    self._log(f'=> Setting voxel size to {self.voxel_size}')
+
+    num_feats = 1
+    try:
+      FCGFModel = load_model(network_config['feat_model'])
+      self.fcgf_model = FCGFModel(num_feats, network_config['feat_model_n_out'],
+                                  bn_momentum=network_config['bn_momentum'],
+                                  conv1_kernel_size=network_config['feat_conv1_kernel_size'],
+                                  normalize_feature=network_config['normalize_feature'])
+    except KeyError:                # legacy pretrained models
+      FCGFModel = load_model(network_config['model'])
+      self.fcgf_model = FCGFModel(num_feats, network_config['model_n_out'],
+                                  bn_momentum=network_config['bn_momentum'],
+                                  conv1_kernel_size=network_config['conv1_kernel_size'],
+                                  normalize_feature=network_config['normalize_feature'])
+    self.fcgf_model.load_state_dict(state['state_dict'])
+    self.fcgf_model = self.fcgf_model.to(self.device).eval()
+
+    num_feats = 6 if network_config.inlier_feature_type == 'coords' else 1
+    InlierModel = load_model(network_config['inlier_model'])
+    self.inlier_model = InlierModel(num_feats, 1, bn_momentum=network_config['bn_momentum'],
+                                    conv1_kernel_size=network_config['inlier_conv1_kernel_size'],
+                                    normalize_feature=False, D=6)
+    self.inlier_model.load_state_dict(state['state_dict_inlier'])
+    self.inlier_model = self.inlier_model.to(self.device).eval()
+    self._pinned = {}
+    self._log('=> loading finished')
+
+  def _log(self, msg):
+    if self.verbose:
+      print(msg)
+
+  # ---------------------------------------------------------------------------------------
+  def _upload(self, xyz, slot):
+    """numpy -> device through a reused pinned staging buffer (async H2D)."""
+    xyz = np.ascontiguousarray(xyz)
+    if xyz.dtype not in (np.float32, np.float64):
+      xyz = xyz.astype(np.float64)
+    key = (slot, xyz.dtype)
+    buf = self._pinned.get(key)
+    if buf is None or buf.shape[0] < xyz.shape[0]:
+      buf = torch.empty((max(xyz.shape[0], 1), 3), dtype=torch.from_numpy(xyz[:0]).dtype).pin_memory()
+      self._pinned[key] = buf
+    view = buf[:xyz.shape[0]]
+    view.numpy()[...] = xyz
+    return view.to(self.device, non_blocking=True)
+
+  def preprocess(self, pcd, _slot=0):
+    """Stage 0: voxelise.  -> (xyz float32 [N,3], coords int32 [N,4], feats [N,1]).
+    One GPU pass replaces sparse_quantize + the re-flooring of the reference (:134-161):
+    floor(xyz / voxel) in the input dtype, first point per voxel, ascending indices."""
+    if isinstance(pcd, np.ndarray):
+      xyz = pcd
+    elif isinstance(pcd, torch.Tensor):
+      xyz = pcd
+    elif hasattr(pcd, 'points'):          # open3d.geometry.PointCloud
+      xyz = np.asarray(pcd.points)
+    else:
+      raise Exception('Unrecognized pcd type')
+    if isinstance(xyz, torch.Tensor):
+      dxyz = xyz.to(self.device).contiguous()
+      if dxyz.dtype not in (torch.float32, torch.float64):
+        dxyz = dxyz.double()
+    else:
+      dxyz = self._upload(xyz, _slot)
+    raw_coords, minmax = _abi.quantize_points(dxyz, self.voxel_size)
+    spec = _abi.keyspec_build(minmax, 4, KEY_MARGIN)
+    table, sel, _, cnt = _abi.unique_first(raw_coords, spec)
+    npts = int(cnt.item())
+    CoordinateManager._check_spec(spec)
+    sel = sel[:npts]
+    coords = _abi.gather_rows_i32(raw_coords, sel, npts)
+    xyz_sel = dxyz[sel.long()].float()
+    # the dedup table already maps voxel key -> row of `coords`: hand it to SparseTensor
+    coords._dgr_manager = CoordinateManager(_parts=(coords, spec, table))
+    self._last_sel = sel
+    feats = torch.ones(npts, 1, device=self.device)
+    return xyz_sel, coords, feats
+
+  def fcgf_feature_extraction(self, feats, coords):
+    """Step 1: FCGF feature per voxel."""
+    sinput = SparseTensor(feats, coordinates=coords, device=self.device)
+    return self.fcgf_model.forward_fused(sinput).F
+
+  def fcgf_feature_matching(self, feats0, feats1):
+    """Step 2: nearest neighbour of every feats0 row in feats1."""
+    idx1 = _abi.knn_top1(feats0.contiguous(), feats1.contiguous())
+    corres_idx0 = torch.arange(len(idx1), device=self.device)
+    return corres_idx0, idx1.long()
+
+  def inlier_feature_generation(self, xyz0, xyz1, coords0, coords1, fcgf_feats0, fcgf_feats1,
+                                corres_idx0, corres_idx1):
+    """Step 3: input features of the inlier network."""
+    assert len(corres_idx0) == len(corres_idx1)
+    feat_type = self.config.inlier_feature_type
+    assert feat_type in ['ones', 'feats', 'coords']
+    corres_idx0 = corres_idx0.to(self.device)
+    corres_idx1 = corres_idx1.to(self.device)
+    if feat_type == 'ones':
+      feat = torch.ones((len(corres_idx0), 1), device=self.device)
+    elif feat_type == 'feats':
+      feat = torch.cat((fcgf_feats0[corres_idx0], fcgf_feats1[corres_idx1]), dim=1)
+    else:
+      feat = torch.cat((torch.cos(xyz0[corres_idx0]), torch.cos(xyz1[corres_idx1])), dim=1)
+    return feat
+
+  def inlier_prediction(self, inlier_feats, coords):
+    """Step 4: inlier logit per correspondence."""
+    sinput = SparseTensor(inlier_feats, coordinates=coords, device=self.device)
+    return self.inlier_model.forward_fused(sinput).F
+
+  def safeguard_registration(self, *args, **kwargs):
+    raise NotImplementedError('the RANSAC safeguard (open3d, core/deep_global_registration.py:50-64) '
+                              'is a "next" row of the build plan and is not built')
+
+  # ---------------------------------------------------------------------------------------
+  def register(self, xyz0, xyz1, inlier_thr=0.00):
+    """Main algorithm.  -> 4x4 float64 ndarray mapping cloud 0 into cloud 1's frame."""
+    self.reg_timer.tic()
+    with torch.no_grad():
+      xyz0, coords0, feats0 = self.preprocess(xyz0, 0)
+      xyz1, coords1, feats1 = self.preprocess(xyz1, 1)
+
+      self.feat_timer.tic()
+      fcgf_feats0 = self.fcgf_feature_extraction(feats0, coords0)
+      fcgf_feats1 = self.fcgf_feature_extraction(feats1, coords1)
+      self.feat_timer.toc()
+
+      idx1 = _abi.knn_top1(fcgf_feats0, fcgf_feats1)              # int32 [N0]
+      inlier_coords = _abi.inlier_coords(coords0, coords1, idx1)    # int32 [N0, 7]
+      feat_type = self.config.inlier_feature_type
+      if feat_type == 'ones':
+        inlier_feats = torch.ones((len(idx1), 1), device=self.device)
+      else:
+        corres_idx0 = torch.arange(len(idx1), device=self.device)
+        inlier_feats = self.inlier_feature_generation(xyz0, xyz1, coords0, coords1, fcgf_feats0,
+                                                      fcgf_feats1, corres_idx0, idx1.long())
+      logit = self.inlier_prediction(inlier_feats.contiguous(), coords=inlier_coords)
+      weights, wsum_dev = _abi.sigmoid_clip_sum(logit, self.clip_weight_thresh)
+      wsum = float(wsum_dev.item())
+
+    wsum_threshold = max(200, len(weights) * 0.05)
+    sign = '>=' if wsum >= wsum_threshold else '<'
+    self._log(f'=> Weighted sum {wsum:.2f} {sign} threshold {wsum_threshold}')
+
+    T = np.identity(4)
+    self.last_info = dict(wsum=wsum, n0=len(weights), n1=len(xyz1))
+    if wsum >= wsum_threshold:
+      res = _abi.se3_register(xyz0, xyz1, weights.reshape(-1), idx1=idx1,
+                              quantization_size=2 * self.voxel_size, max_iter=1000, max_break_count=20,
+                              break_threshold_ratio=1e-4).cpu().numpy()
+      T[0:3, 0:3] = res[:9].reshape(3, 3)
+      T[0:3, 3] = res[9:12]
+      self.last_branch = 'procrustes'
+      self.last_info.update(iterations=int(res[12]), loss=float(res[13]), break_count=int(res[14]),
+                            n_active=int(res[15]))
+      dgr_time = self.reg_timer.toc()
+      self._log(f'=> DGR takes {dgr_time:.2} s')
+    else:
+      self.last_branch = 'safeguard'
+      self.reg_timer.toc()
+      self._log('=> weight sum below threshold: the reference falls back to open3d RANSAC here; the '
+                'safeguard is not built, returning identity')
+    if self.use_icp:
+      raise NotImplementedError('ICP refinement (open3d, core/deep_global_registration.py:317-322) is a '
+                                '"next" row of the build plan and is not built')
+    return T

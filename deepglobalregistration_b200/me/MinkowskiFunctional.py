@@ -1,0 +1,7 @@
+"""ME.MinkowskiFunctional: only ``relu`` is on the hot path (model/resunet.py:602-640,
+model/residual_block.py:123,132)."""
+from .. import _abi
+
+
+def relu(x, *a, **k):
+  return x._like(_abi.affine_act(x.F, relu=True))

@@ -1,0 +1,197 @@
+/*
+ * dgr_b200.h - C ABI of libdgr_b200.so: the B200-native (sm_100a) replacement for the
+ * native layer underneath Deep Global Registration's pairwise-registration hot path.
+ *
+ * The reference (chrischoy/DeepGlobalRegistration) has no native code of its own; the
+ * native layer on this path is the pybind11 module of MinkowskiEngine 0.5.4
+ * (requirements.txt:24) plus a handful of ATen / LAPACK kernels reached through torch.
+ * Every entry point below names the reference call site it serves.
+ *
+ * Conventions
+ *   - plain C, no torch types: raw device pointers + extents; the caller owns every
+ *     buffer (inputs, outputs, workspaces); the library never allocates, frees or
+ *     retains memory beyond one call;
+ *   - every function enqueues its work on `stream` (a cudaStream_t passed as void*)
+ *     and returns without synchronising, unless stated otherwise;
+ *   - return value 0 = OK, negative = error; dgr_last_error() returns a thread-local
+ *     message for the last failing call;
+ *   - all row indices are int32; feature matrices are row-major float32 [rows, channels];
+ *     coordinate matrices are row-major int32 [rows, ncols] with column 0 = batch index
+ *     (ME.utils.batched_coordinates layout, core/deep_global_registration.py:158);
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute
+ *     entry point fails with DGR_ERR_DEVICE.
+ */
+#ifndef DGR_B200_H_
+#define DGR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGR_OK 0
+#define DGR_ERR_CUDA (-1)
+#define DGR_ERR_ARG (-2)
+#define DGR_ERR_DEVICE (-3)
+
+#define DGR_MAX_COLS 8      /* batch + up to 7 spatial columns (DGR uses 4 and 7) */
+
+/* Packing rule of one coordinate row into a 64-bit hash key:
+ *   key = sum_i (uint64)(c[i] - lo[i]) << shift[i]
+ * Lives in DEVICE memory (written by dgr_keyspec_build, read by every kernel that hashes
+ * coordinates) so that building it costs no host round trip.  `overflow` != 0 means the
+ * coordinate extent does not fit 63 bits and every later result is invalid; the host
+ * checks it at its next natural synchronisation point and raises. */
+typedef struct dgr_keyspec {
+  int32_t ncols;
+  int32_t overflow;
+  int32_t lo[DGR_MAX_COLS];
+  int32_t shift[DGR_MAX_COLS];
+  int32_t bits[DGR_MAX_COLS];
+} dgr_keyspec_t;
+
+/* ---- library ------------------------------------------------------------------------ */
+int32_t dgr_version(void);
+const char* dgr_last_error(void);
+/* 0 if device `device` is sm_100 (B200); DGR_ERR_DEVICE otherwise.  Host-only query. */
+int32_t dgr_device_check(int32_t device);
+
+/* ---- voxelisation: ME.utils.sparse_quantize + re-floor of preprocess()
+ *      (core/deep_global_registration.py:152-158) ------------------------------------- */
+/* coords[r] = (batch, floor(xyz[r] / voxel)) with the division in the input dtype
+ * (is_f64 ? double : float), plus per-column min/max into minmax[2*4] (device int32:
+ * mins then maxes; initialised by the call). */
+int32_t dgr_quantize_points(const void* xyz, int32_t is_f64, int64_t n, double voxel, int32_t batch,
+                            int32_t* coords, int32_t* minmax, void* stream);
+/* Per-column min/max of an existing coordinate matrix into minmax[2*ncols]. */
+int32_t dgr_coords_minmax(const int32_t* coords, int64_t n, int32_t ncols, int32_t* minmax,
+                          void* stream);
+/* Key spec from min/max with `margin` spare cells on both sides of every spatial axis
+ * (kernel offsets and coarser strides stay inside the packed range). */
+int32_t dgr_keyspec_build(const int32_t* minmax, int32_t ncols, int32_t margin, dgr_keyspec_t* spec,
+                          void* stream);
+
+/* ---- coordinate hash: ME CoordinateMap insert / find (ME.SparseTensor(...),
+ *      core/deep_global_registration.py:167,214) ------------------------------------- */
+/* keys[cap] (uint64) / vals[cap] (int32) open-addressing table, cap a power of two. */
+int32_t dgr_hash_clear(uint64_t* keys, int32_t* vals, int64_t cap, void* stream);
+/* Deduplicate rows keeping the FIRST occurrence (smallest row index) of every distinct
+ * coordinate, deterministically:
+ *   sel[0..m)      ascending first-occurrence rows,
+ *   inverse[n]     row -> index into sel of its representative,
+ *   *n_unique      m (device int32),
+ * and leaves the table mapping key -> index into sel.  slot_ws[n], rank_ws[n] and
+ * scan_ws[dgr_scan_ws_elems(n)] are int32 workspaces. */
+int32_t dgr_unique_first(const int32_t* coords, int64_t n, int32_t ncols, const dgr_keyspec_t* spec,
+                         uint64_t* keys, int32_t* vals, int64_t cap, int32_t* sel, int32_t* inverse,
+                         int32_t* n_unique, int32_t* slot_ws, int32_t* rank_ws, int32_t* scan_ws,
+                         void* stream);
+int64_t dgr_scan_ws_elems(int64_t n);
+/* rows[i] -> vals of matching key, or -1. */
+int32_t dgr_hash_find(const int32_t* coords, int64_t n, int32_t ncols, const dgr_keyspec_t* spec,
+                      const uint64_t* keys, const int32_t* vals, int64_t cap, int32_t* rows_out,
+                      void* stream);
+/* out[i, :] = src[idx[i], :] for int32 row matrices. */
+int32_t dgr_gather_rows_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t ncols,
+                            int32_t* out, void* stream);
+
+/* ---- strided coordinate maps: ME stride-2 convolution output map
+ *      (model/resunet.py:461-507 conv2/conv3/conv4) --------------------------------- */
+/* out[r, 0] = in[r, 0]; out[r, c] = floor_div(in[r, c], out_stride) * out_stride. */
+int32_t dgr_stride_coords(const int32_t* coords, int64_t n, int32_t ncols, int32_t out_stride,
+                          int32_t* out, void* stream);
+
+/* ---- kernel maps: ME kernel_map for KernelGenerator(kernel_size, HYPER_CUBE)
+ *      (model/residual_block.py:31-44,56-80) ----------------------------------------- */
+/* nbr[kappa * n_out + j] = row i of the input map with C_in[i] == C_out[j] + offsets[kappa]
+ * or -1.  offsets is a DEVICE int32 [K, ncols-1] matrix (already scaled by the input
+ * tensor stride), kappa enumerates axis 0 fastest. */
+int32_t dgr_kernel_map_table(const int32_t* out_coords, int64_t n_out, int32_t ncols,
+                             const dgr_keyspec_t* spec, const uint64_t* in_keys,
+                             const int32_t* in_vals, int64_t in_cap, const int32_t* offsets,
+                             int32_t K, int32_t* nbr, void* stream);
+/* Pair lists sorted by (kappa, j): two calls around one host read of kofs[K] (= P).
+ *   count: kofs[K+1] exclusive offsets of every bucket (device int32), block_ws
+ *          workspace of dgr_kmap_ws_elems(K, n_out) int32;
+ *   fill : in_idx[P], out_idx[P]. */
+int64_t dgr_kmap_ws_elems(int32_t K, int64_t n_out);
+int32_t dgr_kernel_map_count(const int32_t* nbr, int32_t K, int64_t n_out, int32_t* block_ws,
+                             int32_t* kofs, void* stream);
+int32_t dgr_kernel_map_fill(const int32_t* nbr, int32_t K, int64_t n_out, const int32_t* block_ws,
+                            int32_t* in_idx, int32_t* out_idx, void* stream);
+/* Work list of the gather-GEMM-scatter kernel: tile t covers pairs
+ * [tile_start[t], min(tile_start[t] + tile_rows, kofs[tile_k[t] + 1])) of bucket tile_k[t].
+ * n_tiles = sum_k ceil(count_k / tile_rows) is computed by the caller from kofs. */
+int32_t dgr_kernel_map_tiles(const int32_t* kofs, int32_t K, int32_t tile_rows, int32_t n_tiles,
+                             int32_t* tile_k, int32_t* tile_start, void* stream);
+
+/* ---- sparse convolution forward: ME.MinkowskiConvolution / ConvolutionTranspose
+ *      (model/residual_block.py:38-44,72-80; graph model/resunet.py:598-649) ---------- */
+/* out[out_idx[p], :] += in[in_idx[p], :] @ W[kappa(p)]   for all pairs p.
+ * `out` must hold the initial value (zeros, or a bias/residual to accumulate onto).
+ * W is [K, cin, cout] row-major fp32 (ME's `kernel` parameter layout).  A transposed
+ * convolution passes the down-convolution's lists with in_idx/out_idx exchanged.
+ * relu_in != 0 applies max(x, 0) to gathered input rows (fuses a preceding MEF.relu). */
+int32_t dgr_spconv_fwd(const float* in_feat, int32_t cin, const float* weight, int32_t cout,
+                       const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,
+                       const int32_t* tile_k, const int32_t* tile_start, int32_t n_tiles,
+                       int32_t tile_rows, int32_t relu_in, float* out, void* stream);
+/* Output-stationary variant for few input channels (conv1: cin == 1): reads the dense
+ * neighbour table, no atomics, optional fused per-channel affine (eval BatchNorm):
+ *   out[j, :] = (sum_kappa in[nbr[kappa, j], :] @ W[kappa]) * scale + shift. */
+int32_t dgr_spconv_table_fwd(const float* in_feat, int32_t cin, const float* weight, int32_t cout,
+                             const int32_t* nbr, int32_t K, int64_t n_out, const float* scale,
+                             const float* shift, float* out, void* stream);
+/* kernel_size == 1 convolution (conv1_tr / final, model/resunet.py:578-596):
+ *   out = act((concat(a, b) @ W[ca+cb, cout]) + bias), b may be NULL (cb = 0): fuses ME.cat.
+ * relu != 0 applies ReLU; normalize != 0 divides every row by (||row||_2 + 1e-8)
+ * (model/resunet.py:643-647) and requires cout <= 64. */
+int32_t dgr_linear_fwd(const float* a, int32_t ca, const float* b, int32_t cb, int64_t n,
+                       const float* weight, int32_t cout, const float* bias, int32_t relu,
+                       int32_t normalize, float* out, void* stream);
+
+/* ---- elementwise layers ------------------------------------------------------------ */
+/* out = act(x * scale[c] + shift[c] + residual): eval-mode ME.MinkowskiBatchNorm
+ * (model/common.py:13) folded to scale/shift, the residual add and MEF.relu of
+ * BasicBlockBase.forward (model/residual_block.py:118-134).  scale/shift/residual may be
+ * NULL; out may alias x. */
+int32_t dgr_affine_act(const float* x, int64_t n, int32_t c, const float* scale, const float* shift,
+                       const float* residual, int32_t relu, float* out, void* stream);
+/* ME.cat(a, b): out[:, :ca] = a, out[:, ca:] = b (model/resunet.py:624,631,638). */
+int32_t dgr_cat2(const float* a, int32_t ca, const float* b, int32_t cb, int64_t n, float* out,
+                 void* stream);
+/* F / (||F||_2 + 1e-8) row-wise (model/resunet.py:643-647). */
+int32_t dgr_l2_normalize(const float* x, int64_t n, int32_t c, float* out, void* stream);
+
+/* ---- feature nearest neighbour: find_knn_gpu(knn=1) (core/knn.py:23-74) with pdist
+ *      'L2' (core/metrics.py:62-65) ---------------------------------------------------- */
+/* idx[i] = argmin_j sqrt(sum_c (F0[i,c]-F1[j,c])^2 + 1e-7), lowest j on ties.
+ * packed_ws[n0] is a uint64 workspace; dist (optional) receives the minimum. */
+int32_t dgr_knn_top1(const float* f0, int64_t n0, const float* f1, int64_t n1, int32_t c,
+                     uint64_t* packed_ws, int32_t* idx, float* dist, void* stream);
+
+/* ---- correspondences -> 6-D coordinates, weights (core/deep_global_registration.py:261-272) */
+/* out[i] = (coords0[i, 0..3], coords1[idx1[i], 1..3]) int32 [n0, 7]. */
+int32_t dgr_inlier_coords(const int32_t* coords0, const int32_t* coords1, const int32_t* idx1,
+                          int64_t n0, int32_t* out, void* stream);
+/* w = sigmoid(logit); w[w < clip] = 0 (if clip > 0); *wsum (device double) = sum w. */
+int32_t dgr_sigmoid_clip_sum(const float* logit, int64_t n, float clip, float* w, double* wsum,
+                             void* stream);
+
+/* ---- weighted Procrustes + SE(3) refinement (core/registration.py:91-113,135-194,
+ *      core/loss.py:42-61) -------------------------------------------------------------- */
+/* Correspondence i pairs x[i] with y[idx1[i]] (idx1 may be NULL: y[i]).
+ * result (device float[16]): R row-major [0..9), t [9..12), iterations, final loss,
+ * break_count, n_active (correspondences with non-zero weight).
+ * max_iter == 0 returns the closed-form weighted Procrustes solution only.
+ * pack_ws: float workspace of 7 * n elements; cnt_ws: int32[4]. */
+int32_t dgr_se3_register(const float* x, const float* y, const int32_t* idx1, const float* w,
+                         int64_t n, float quantization_size, int32_t max_iter,
+                         int32_t max_break_count, float break_threshold_ratio, float lr, float gamma,
+                         float* pack_ws, int32_t* cnt_ws, float* result, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGR_B200_H_ */

@@ -1,0 +1,119 @@
+"""End-to-end and stage-isolated parity of DeepGlobalRegistration.register() against the
+CPU oracle (oracle/pipeline.py) on small synthetic pairs.
+
+Tolerances (north_star): voxel / correspondence indices bit-exact (correspondences outside
+the fp64 ambiguity band), features / weights within 5e-5 relative, R,t within 1e-3 rad /
+1e-3 m."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from deepglobalregistration_b200 import synthetic as syn
+from oracle import pipeline as op
+from oracle import registration as oreg
+
+pytestmark = pytest.mark.gpu
+EXTENT = (1.8, 1.5, 1.25)
+
+
+@pytest.fixture(scope='module')
+def state():
+  return syn.make_checkpoint(0)
+
+
+@pytest.fixture(scope='module')
+def dgr(state):
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+  cfg = types.SimpleNamespace(weights=state, clip_weight_thresh=0.05, verbose=False)
+  return DeepGlobalRegistration(cfg, device=torch.device('cuda'))
+
+
+def _rel(got, want):
+  got, want = got.detach().cpu().double(), want.detach().cpu().double()
+  return float(((got - want).abs() / (1 + want.abs())).max())
+
+
+def test_stage_isolated_parity(dgr, state):
+  xyz0, xyz1, _ = syn.room_pair(0, n_raw=20000, extent=EXTENT)
+  T_o, taps = op.register(state, xyz0, xyz1)
+  with torch.no_grad():
+    # stage 0: voxelisation - bit exact
+    p0, c0, f0 = dgr.preprocess(xyz0, 0)
+    sel0 = dgr._last_sel.cpu().numpy()
+    p1, c1, f1 = dgr.preprocess(xyz1, 1)
+    assert np.array_equal(sel0, taps['sel0'])
+    assert np.array_equal(c0.cpu().numpy(), taps['coords0']) and np.array_equal(c1.cpu().numpy(), taps['coords1'])
+    assert np.array_equal(p0.cpu().numpy(), taps['xyz0'])
+    # stage 1: FCGF features
+    F0 = dgr.fcgf_feature_extraction(f0, c0)
+    F1 = dgr.fcgf_feature_extraction(f1, c1)
+    assert _rel(F0, taps['feat0']) <= 5e-5 and _rel(F1, taps['feat1']) <= 5e-5
+    # stage 2: kNN on the ORACLE's features - indices exact outside the ambiguity band
+    i0, i1 = dgr.fcgf_feature_matching(taps['feat0'].cuda(), taps['feat1'].cuda())
+    want, amb = oreg.feature_knn(taps['feat0'], taps['feat1'], return_ambiguous=True)
+    assert i1.dtype == torch.int64 and torch.equal(i0.cpu(), torch.arange(len(want)))
+    ok = (i1.cpu() == want) | amb
+    assert bool(ok.all()), f'{int((~ok).sum())} kNN mismatches outside the ambiguity band'
+    # stage 3/4: 6-D coords + inlier net on the ORACLE's correspondences
+    from deepglobalregistration_b200 import _abi
+    idx1 = torch.from_numpy(taps['idx1']).int().cuda()
+    c6 = _abi.inlier_coords(c0, c1, idx1)
+    assert np.array_equal(c6.cpu().numpy(), taps['coords6'])
+    logit = dgr.inlier_prediction(torch.ones(len(idx1), 1, device='cuda'), c6)
+    assert _rel(logit, taps['logit']) <= 5e-5
+    # stage 5: registration on the ORACLE's weights
+    w = taps['weights'].cuda().reshape(-1).contiguous()
+    res = _abi.se3_register(p0, p1, w, idx1=idx1, quantization_size=2 * dgr.voxel_size,
+                            break_threshold_ratio=1e-4).cpu().numpy()
+  T = np.eye(4)
+  T[:3, :3], T[:3, 3] = res[:9].reshape(3, 3), res[9:12]
+  if taps['branch'] == 'procrustes':
+    te, re = syn.rte_rre(T, T_o)
+    assert te <= 1e-3 and re <= 1e-3, (te, re, res[12:], taps['refine'])
+
+
+def test_register_known_answer_rigid_copy(dgr, state):
+  """Cloud 1 = cloud 0 shifted by whole voxels: exact correspondences, exact answer."""
+  xyz0, xyz1, T_gt = syn.room_pair(1, n_raw=20000, extent=EXTENT, rigid_copy=True)
+  T = dgr.register(xyz0, xyz1)
+  assert dgr.last_branch == 'procrustes'
+  te, re = syn.rte_rre(T, T_gt)
+  assert te <= 1e-3 and re <= 1e-3, (te, re, dgr.last_info)
+  T_o, taps = op.register(state, xyz0, xyz1)
+  te, re = syn.rte_rre(T, T_o)
+  assert te <= 1e-3 and re <= 1e-3, (te, re)
+  assert T.dtype == np.float64 and T.shape == (4, 4)
+
+
+def test_register_end_to_end_vs_oracle(dgr, state):
+  xyz0, xyz1, _ = syn.room_pair(2, n_raw=20000, extent=EXTENT)
+  T = dgr.register(xyz0, xyz1)
+  T_o, taps = op.register(state, xyz0, xyz1)
+  assert dgr.last_branch == taps['branch']
+  assert abs(dgr.last_info['wsum'] - taps['wsum']) <= 1e-3 * max(1.0, taps['wsum'])
+  if taps['branch'] == 'procrustes':
+    te, re = syn.rte_rre(T, T_o)
+    # random-init features give ill-conditioned correspondences; the documented end-to-end
+    # bar applies (1e-3 rad / 1e-3 m) and holds because every stage matches to ~1e-5.
+    assert te <= 1e-3 and re <= 1e-3, (te, re, dgr.last_info, taps['refine'])
+
+
+def test_register_float32_and_lidar_shape(dgr, state):
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+  st = syn.make_checkpoint(3, voxel_size=0.3, feat_conv1_kernel_size=5)
+  cfg = types.SimpleNamespace(weights=st, clip_weight_thresh=0.05, verbose=False)
+  d = DeepGlobalRegistration(cfg)
+  xyz0, xyz1, _ = syn.lidar_pair(0)
+  xyz0, xyz1 = xyz0[::4].astype(np.float32), xyz1[::4].astype(np.float32)
+  with torch.no_grad():
+    p0, c0, _ = d.preprocess(xyz0)
+  oc, osel = op.so.quantize_first(xyz0, 0.3)
+  assert np.array_equal(c0.cpu().numpy()[:, 1:], oc)
+  T = d.register(xyz0, xyz1)
+  T_o, taps = op.register(st, xyz0, xyz1)
+  assert d.last_branch == taps['branch']
+  if taps['branch'] == 'procrustes':
+    te, re = syn.rte_rre(T, T_o)
+    assert te <= 1e-3 and re <= 1e-3, (te, re)
