@@ -121,18 +121,20 @@ def room_scan(seed, n_raw=250_000, extent=(3.6, 3.0, 2.5), scene_seed=None, nois
   return _sample_boxes(boxes, n_raw, rng, noise)
 
 
-def room_pair(seed, n_raw=250_000, extent=(3.6, 3.0, 2.5), rigid_copy=False):
+def room_pair(seed, n_raw=250_000, extent=(3.6, 3.0, 2.5), rigid_copy=False, voxel_size=0.0625):
   """(xyz0, xyz1, T_gt) float64 with T_gt mapping cloud 0 into cloud 1's frame.
 
   rigid_copy=False: the same surfaces re-sampled with another seed, then moved by
   a random SE(3) (<=45 deg, <=0.5 m).  rigid_copy=True: cloud 1 is cloud 0
-  translated by a whole number of 5 cm voxels, the known-answer case in which a
-  translation-equivariant network yields exact correspondences."""
+  translated by a multiple of 8 voxels (the network's coarsest tensor stride, so the
+  strided lattices of both clouds align; use a power-of-two voxel size so the shift is
+  exact in binary) - the known-answer case in which identical neighbourhoods yield
+  identical features, exact correspondences and therefore the exact transform."""
   xyz0 = room_scan(2 * seed, n_raw, extent, scene_seed=seed)
   rng = np.random.default_rng(777 + seed)
   if rigid_copy:
     T = np.eye(4)
-    T[:3, 3] = 0.05 * rng.integers(-6, 7, size=3)
+    T[:3, 3] = voxel_size * 8 * rng.integers(-3, 4, size=3)
     return xyz0, apply_se3(T, xyz0), T
   T = random_se3(rng)
   xyz1 = apply_se3(T, room_scan(2 * seed + 1, n_raw, extent, scene_seed=seed))

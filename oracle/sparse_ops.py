@@ -155,7 +155,13 @@ def linear_forward(feat, weight, bias=None, dtype=torch.float32):
   return out
 
 
-def batchnorm_eval(feat, sd, prefix, dtype=torch.float32):
+def batchnorm_eval(feat, sd, prefix, dtype=torch.float32, calibrate=False):
+  if calibrate:      # record the input statistics as running statistics (util/calibrate.py twin)
+    x = feat.float()
+    sd[prefix + '.bn.running_mean'] = x.mean(0)
+    sd[prefix + '.bn.running_var'] = x.var(0, unbiased=False).clamp_min(1e-6)
+    sd[prefix + '.bn.weight'] = torch.ones(x.shape[1])
+    sd[prefix + '.bn.bias'] = torch.zeros(x.shape[1])
   w = sd[prefix + '.bn.weight'].to(dtype)
   b = sd[prefix + '.bn.bias'].to(dtype)
   m = sd[prefix + '.bn.running_mean'].to(dtype)

@@ -74,14 +74,35 @@ def test_stage_isolated_parity(dgr, state):
     assert te <= 1e-3 and re <= 1e-3, (te, re, res[12:], taps['refine'])
 
 
-def test_register_known_answer_rigid_copy(dgr, state):
-  """Cloud 1 = cloud 0 shifted by whole voxels: exact correspondences, exact answer."""
-  xyz0, xyz1, T_gt = syn.room_pair(1, n_raw=20000, extent=EXTENT, rigid_copy=True)
-  T = dgr.register(xyz0, xyz1)
-  assert dgr.last_branch == 'procrustes'
+def test_register_known_answer_rigid_copy():
+  """Cloud 1 = cloud 0 shifted by a multiple of 8 voxels - the coarsest tensor stride, so the
+  strided lattices of both clouds align - with voxel = 2^-4 m so the shift is exact in
+  binary: identical neighbourhoods give identical features, hence exact correspondences,
+  hence the exact transform - provided the features have contrast, which a random-init
+  checkpoint only has after BatchNorm calibration (util/calibrate.py)."""
+  from deepglobalregistration_b200 import me as ME
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+  from deepglobalregistration_b200.util.calibrate import calibrate_batchnorm
+  vs = 0.0625
+  st = syn.make_checkpoint(4, voxel_size=vs)
+  cfg = types.SimpleNamespace(weights=st, clip_weight_thresh=0.05, verbose=False)
+  d = DeepGlobalRegistration(cfg)
+  xyz0 = syn.room_scan(2, 20000, EXTENT, scene_seed=1)
+  T_gt = np.eye(4)
+  shift = np.array([8, -16, 24])
+  T_gt[:3, 3] = vs * shift
+  xyz1 = syn.apply_se3(T_gt, xyz0)
+  with torch.no_grad():
+    _, c0, f0 = d.preprocess(xyz0)
+    calibrate_batchnorm(d.fcgf_model, ME.SparseTensor(f0, coordinates=c0, device='cuda'))
+  st['state_dict'] = {k: v.detach().cpu().clone() for k, v in d.fcgf_model.state_dict().items()}
+  T = d.register(xyz0, xyz1)
+  assert d.last_branch == 'procrustes'
   te, re = syn.rte_rre(T, T_gt)
-  assert te <= 1e-3 and re <= 1e-3, (te, re, dgr.last_info)
-  T_o, taps = op.register(state, xyz0, xyz1)
+  assert te <= 1e-3 and re <= 1e-3, (te, re, d.last_info)
+  T_o, taps = op.register(st, xyz0, xyz1)
+  exact = (taps['coords1'][taps['idx1'], 1:] - taps['coords0'][:, 1:] == shift).all(1)
+  assert exact.mean() > 0.99, exact.mean()
   te, re = syn.rte_rre(T, T_o)
   assert te <= 1e-3 and re <= 1e-3, (te, re)
   assert T.dtype == np.float64 and T.shape == (4, 4)
