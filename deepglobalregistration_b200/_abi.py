@@ -46,6 +46,9 @@ SIGNATURES = {
     'dgr_kernel_map_fill': [_p, _i32, _i64, _p, _p, _p, _p],
     'dgr_kernel_map_tiles': [_p, _i32, _i32, _i32, _p, _p, _p],
     'dgr_spconv_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
+    'dgr_spconv_tc_supported': [_i32, _i32],
+    'dgr_transpose_weight': [_p, _i32, _i32, _i32, _p, _p],
+    'dgr_spconv_tc_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
     'dgr_spconv_table_fwd': [_p, _i32, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p],
     'dgr_linear_fwd': [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _i32, _i32, _p, _p],
     'dgr_affine_act': [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p],
@@ -56,7 +59,7 @@ SIGNATURES = {
     'dgr_sigmoid_clip_sum': [_p, _i64, _f32, _p, _p, _p],
     'dgr_se3_register': [_p, _p, _p, _p, _i64, _f32, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p],
 }
-_RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
+_RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
 
 _lib = None
 
@@ -256,6 +259,30 @@ def spconv_fwd(feat, weight, km, out, relu_in=False):
   assert feat.shape[0] == km.n_in and out.shape[0] == km.n_out, (feat.shape, out.shape, km.n_in, km.n_out)
   call('dgr_spconv_fwd', ptr(feat), cin, ptr(weight), cout, ptr(km.in_idx), ptr(km.out_idx), ptr(km.kofs),
        ptr(km.tile_k), ptr(km.tile_start), km.n_tiles, TILE_ROWS, int(relu_in), ptr(out), stream())
+  return out
+
+
+def tc_supported(cin, cout):
+  return bool(lib().dgr_spconv_tc_supported(int(cin), int(cout)))
+
+
+def transpose_weight(weight, K, cin, cout):
+  """[K, cin, cout] -> [K, cout, cin] (the K-major B operand of the tensor-core path)."""
+  _chk(weight, torch.float32, 'weight')
+  wt = torch.empty(K, cout, cin, dtype=torch.float32, device=weight.device)
+  call('dgr_transpose_weight', ptr(weight), K, cin, cout, ptr(wt), stream())
+  return wt
+
+
+def spconv_tc_fwd(feat, weight_t, km, out, passes=3):
+  """Tensor-core gather-GEMM-scatter: out[km.out_idx] += feat[km.in_idx] @ W[kappa]."""
+  _chk(feat, torch.float32, 'feat'); _chk(weight_t, torch.float32, 'weight_t'); _chk(out, torch.float32, 'out')
+  cin, cout = feat.shape[1], out.shape[1]
+  assert weight_t.numel() == km.K * cin * cout
+  assert feat.shape[0] == km.n_in and out.shape[0] == km.n_out
+  call('dgr_spconv_tc_fwd', ptr(feat), cin, ptr(weight_t), cout, ptr(km.in_idx), ptr(km.out_idx),
+       ptr(km.kofs), ptr(km.tile_k), ptr(km.tile_start), km.n_tiles, TILE_ROWS, int(passes), ptr(out),
+       stream())
   return out
 
 

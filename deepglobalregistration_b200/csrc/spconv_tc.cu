@@ -1,0 +1,378 @@
+// Sparse convolution forward on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Same contract as dgr_spconv_fwd (gather -> per-offset sub-GEMM -> scatter-add over the
+// (kappa, j)-sorted pair lists) with the sub-GEMM issued as tcgen05.mma kind::tf32 and the
+// accumulator in tensor memory:
+//
+//   * one work item = one 128-pair tile of one kernel offset, M = 128 rows (pairs),
+//     N = cout (16..256), K = cin in chunks of 32 floats (one 128-byte swizzle row);
+//   * 4 loader warps gather the 128 input rows (coalesced 16-byte pieces, 8 lanes per row),
+//     and stream the [cout x 32] slab of the offset's weight matrix, split every fp32 value
+//     into a TF32 "hi" part and a TF32 "lo" residual in registers, and store both into
+//     shared memory in the canonical K-major SWIZZLE_128B layout;
+//   * one elected thread of warp 4 issues, per 8-wide k-step, the three products
+//     hi*hi + lo*hi + hi*lo (3xTF32: fp32-accurate to ~2^-21 relative) into TMEM;
+//     tcgen05.commit on an mbarrier frees the shared-memory stage / publishes the tile;
+//   * the loader warps then read the accumulator with tcgen05.ld (warp w owns TMEM lanes
+//     32w..32w+31 = pairs 32w..) and scatter-add rows with red.global.add.v4.f32.
+//
+// CTAs are persistent (grid = resident CTAs); stages are mbarrier-pipelined so the gather
+// of chunk c+1 overlaps the MMAs of chunk c.  Weights are expected TRANSPOSED per offset,
+// [K, cout, cin] (K-major B operand); the host caches that layout per layer.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kLoaderThreads = 128;
+constexpr int kThreadsTC = 160;          // 4 loader/epilogue warps + 1 MMA warp
+constexpr int kTileM = 128;
+constexpr int kChunk = 32;               // floats of K per stage (128 bytes)
+constexpr int kATileBytes = kTileM * 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major SWIZZLE_128B operand descriptor: 8-row groups of 128-byte rows, 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+
+// split one float4 into tf32 hi / lo and store both at the swizzled 16-byte slot
+__device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, unsigned char* lo_tile, int row,
+                                            int piece) {
+  float4 h, l;
+  h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+  l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y);
+  l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
+  const int off = row * 128 + ((piece ^ (row & 7)) << 4);
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+struct TcShared {
+  unsigned long long full[4];
+  unsigned long long empty[4];
+  unsigned long long acc_full;
+  uint32_t tmem_base;
+  int s_in[kTileM];
+  int s_out[kTileM];
+};
+
+__global__ void __launch_bounds__(kThreadsTC, 2)
+spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __restrict__ wt, int cout,
+                 const int32_t* __restrict__ in_idx, const int32_t* __restrict__ out_idx,
+                 const int32_t* __restrict__ kofs, const int32_t* __restrict__ tile_k,
+                 const int32_t* __restrict__ tile_start, int n_tiles, int n_stages, int tmem_cols,
+                 int passes, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  TcShared& sh = *reinterpret_cast<TcShared*>(smem_dyn);
+  // stage buffers start at the next 1024-byte boundary (SWIZZLE_128B atom alignment)
+  unsigned char* stage0 = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + sizeof(TcShared) + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = cout * 128;
+  const int stage_bytes = 2 * kATileBytes + 2 * b_tile_bytes;
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int n_chunks = cin / kChunk;
+
+  if (t == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(smem_u32(&sh.full[s]), kLoaderThreads);
+      mbar_init(smem_u32(&sh.empty[s]), 1);
+    }
+    mbar_init(smem_u32(&sh.acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&sh.tmem_base)),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_base;
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = cout, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cout >> 3) << 17) |
+                         ((uint32_t)(kTileM >> 4) << 24);
+
+  uint32_t it = 0;        // global chunk counter of this CTA (same sequence in both roles)
+  uint32_t tile_iter = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+    const int kappa = tile_k[tile];
+    const int p0 = tile_start[tile];
+    const int rows = min(kTileM, kofs[kappa + 1] - p0);
+    if (warp < 4) {
+      // ------------------------------ loaders ------------------------------------------
+      if (t < kTileM) {
+        const bool ok = t < rows;
+        sh.s_in[t] = ok ? in_idx[p0 + t] : -1;
+        sh.s_out[t] = ok ? out_idx[p0 + t] : -1;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* wk = wt + (size_t)kappa * cout * cin;
+      const int piece = t & 7, rgrp = t >> 3;
+      for (int c = 0; c < n_chunks; ++c, ++it) {
+        const int s = it % n_stages;
+        const uint32_t ph = (it / n_stages) & 1;
+        mbar_wait(smem_u32(&sh.empty[s]), ph ^ 1);
+        unsigned char* a_hi = stage0 + (size_t)s * stage_bytes;
+        unsigned char* a_lo = a_hi + kATileBytes;
+        unsigned char* b_hi = a_lo + kATileBytes;
+        unsigned char* b_lo = b_hi + b_tile_bytes;
+        const int c0 = c * kChunk + piece * 4;
+        // A: 128 gathered rows, 8 per thread
+        float4 av[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 16 + rgrp;
+          const int src = sh.s_in[r];
+          av[i] = src >= 0 ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)src * cin + c0))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // B: cout rows of the transposed weight slab, cout / 16 per thread
+        for (int i0 = 0; i0 < cout / 16; i0 += 8) {
+          float4 bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (i0 + i) * 16 + rgrp;
+            if (i0 + i < cout / 16)
+              bv[i] = __ldg(reinterpret_cast<const float4*>(wk + (size_t)r * cin + c0));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i0 + i < cout / 16) split_store(bv[i], b_hi, b_lo, (i0 + i) * 16 + rgrp, piece);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_store(av[i], a_hi, a_lo, i * 16 + rgrp, piece);
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&sh.full[s]));
+      }
+      // ------------------------------ epilogue -----------------------------------------
+      mbar_wait(smem_u32(&sh.acc_full), tile_iter & 1);
+      tc_fence_after();
+      const int j = sh.s_out[warp * 32 + lane];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      int col = 0;
+      for (; col + 32 <= cout; col += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + col, v);
+        if (j >= 0) {
+          float* dst = out + (size_t)j * cout + col;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      if (col < cout) {   // cout % 32 == 16
+        uint32_t v[16];
+        tc_ld16(taddr + col, v);
+        if (j >= 0) {
+          float* dst = out + (size_t)j * cout + col;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // s_in/s_out free, accumulator drained
+    } else {
+      // ------------------------------ MMA issuer ---------------------------------------
+      for (int c = 0; c < n_chunks; ++c, ++it) {
+        const int s = it % n_stages;
+        const uint32_t ph = (it / n_stages) & 1;
+        mbar_wait(smem_u32(&sh.full[s]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_bytes);
+          const uint32_t a_lo = a_hi + kATileBytes;
+          const uint32_t b_hi = a_lo + kATileBytes;
+          const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+          for (int ks = 0; ks < kChunk / 8; ++ks) {
+            const uint32_t ko = ks * 32;   // 8 tf32 = 32 bytes along K inside the swizzle row
+            const uint64_t dah = umma_desc(a_hi + ko), dal = umma_desc(a_lo + ko);
+            const uint64_t dbh = umma_desc(b_hi + ko), dbl = umma_desc(b_lo + ko);
+            tc_mma_tf32(tmem_base, dah, dbh, idesc, (c | ks) != 0);
+            if (passes == 3) {
+              tc_mma_tf32(tmem_base, dal, dbh, idesc, 1);
+              tc_mma_tf32(tmem_base, dah, dbl, idesc, 1);
+            }
+          }
+          tc_commit(smem_u32(&sh.empty[s]));
+          if (c == n_chunks - 1) tc_commit(smem_u32(&sh.acc_full));
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+  }
+}
+
+// [K, cin, cout] -> [K, cout, cin]
+__global__ void transpose_weight_kernel(const float* __restrict__ w, int cin, int cout, float* __restrict__ wt) {
+  __shared__ float tile[32][33];
+  const size_t base = (size_t)blockIdx.z * cin * cout;
+  int ci = blockIdx.y * 32 + threadIdx.y, co = blockIdx.x * 32 + threadIdx.x;
+  if (ci < cin && co < cout) tile[threadIdx.y][threadIdx.x] = w[base + (size_t)ci * cout + co];
+  __syncthreads();
+  co = blockIdx.x * 32 + threadIdx.y;
+  ci = blockIdx.y * 32 + threadIdx.x;
+  if (ci < cin && co < cout) wt[base + (size_t)co * cin + ci] = tile[threadIdx.x][threadIdx.y];
+}
+
+}  // namespace
+
+extern "C" {
+
+// Layout transform the tensor-core path needs once per layer: W[K, cin, cout] -> Wt[K, cout, cin].
+int32_t dgr_transpose_weight(const float* w, int32_t K, int32_t cin, int32_t cout, float* wt, void* stream) {
+  DGR_ARG_CHECK(K >= 1 && cin >= 1 && cout >= 1, "bad weight shape");
+  DGR_ARG_CHECK(K <= 65535, "K too large");
+  dim3 grid((cout + 31) / 32, (cin + 31) / 32, K);
+  transpose_weight_kernel<<<grid, dim3(32, 32), 0, (cudaStream_t)stream>>>(w, cin, cout, wt);
+  DGR_LAUNCH_CHECK();
+  return DGR_OK;
+}
+
+// 1 if dgr_spconv_tc_fwd supports the shape (cin % 32 == 0, cout % 16 == 0, 16 <= cout <= 256).
+int32_t dgr_spconv_tc_supported(int32_t cin, int32_t cout) {
+  return (cin >= 32 && cin % 32 == 0 && cout >= 16 && cout <= 256 && cout % 16 == 0) ? 1 : 0;
+}
+
+// Tensor-core variant of dgr_spconv_fwd.  weight_t is [K, cout, cin] (dgr_transpose_weight).
+// passes = 3: 3xTF32 (fp32-accurate, default); passes = 1: single TF32 product (~1e-3 rel.).
+int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight_t, int32_t cout,
+                          const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,
+                          const int32_t* tile_k, const int32_t* tile_start, int32_t n_tiles,
+                          int32_t tile_rows, int32_t passes, float* out, void* stream) {
+  DGR_ARG_CHECK(tile_rows == kTileM, "tile_rows must be 128");
+  DGR_ARG_CHECK(dgr_spconv_tc_supported(cin, cout), "shape not supported by the tensor-core path");
+  DGR_ARG_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
+  if (n_tiles == 0) return DGR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int stage_bytes = 2 * kATileBytes + 2 * cout * 128;
+  // small layers: <= ~100 KB so that two CTAs share an SM; large layers: fill the SM
+  const int budget = (cout <= 64) ? 100 * 1024 : 200 * 1024;
+  int n_stages = budget / stage_bytes;
+  if (n_stages > 4) n_stages = 4;
+  if (n_stages < 2) n_stages = 2;
+  const int n_chunks = cin / kChunk;
+  if (n_stages > n_chunks + 1 && n_chunks >= 1) n_stages = n_chunks + 1 > 2 ? n_chunks + 1 : 2;
+  if (n_stages > 4) n_stages = 4;
+  const size_t smem = sizeof(TcShared) + 1024 + (size_t)n_stages * stage_bytes;
+  int tmem_cols = 32;
+  while (tmem_cols < cout) tmem_cols <<= 1;
+  DGR_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  int dev = 0, sms = 148;
+  DGR_CUDA_CHECK(cudaGetDevice(&dev));
+  DGR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int per_sm = (int)((220 * 1024) / smem);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm * tmem_cols > 512) per_sm = 512 / tmem_cols;
+  if (per_sm > 4) per_sm = 4;
+  int grid = sms * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  spconv_tc_kernel<<<grid, kThreadsTC, smem, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
+                                                   tile_k, tile_start, n_tiles, n_stages, tmem_cols, passes,
+                                                   out);
+  DGR_LAUNCH_CHECK();
+  return DGR_OK;
+}
+
+}  // extern "C"

@@ -23,6 +23,30 @@ from . import utils  # noqa: F401  (ME.utils.sparse_quantize / batched_coordinat
 
 __version__ = '0.5.4+dgr_b200'
 
+# Arithmetic of the sparse convolution sub-GEMMs:
+#   'tc3'  tcgen05 3xTF32 (hi*hi + lo*hi + hi*lo), fp32-accurate - the default
+#   'tc1'  tcgen05 single TF32 product (~1e-3 relative), opt-in fast mode
+#   'simt' fp32 FFMA kernel (also the fallback for shapes the tensor-core path rejects)
+_CONV_MODE = 'tc3'
+
+
+def set_conv_mode(mode):
+  global _CONV_MODE
+  assert mode in ('tc3', 'tc1', 'simt'), mode
+  _CONV_MODE = mode
+
+
+def get_conv_mode():
+  return _CONV_MODE
+
+
+def sparse_conv(feat, conv_mod, km, out):
+  """out += gather-GEMM-scatter of `feat` through `km` with conv_mod's kernel."""
+  cin, cout = conv_mod.in_channels, conv_mod.out_channels
+  if _CONV_MODE != 'simt' and _abi.tc_supported(cin, cout):
+    return _abi.spconv_tc_fwd(feat, conv_mod.kernel_transposed(), km, out, passes=3 if _CONV_MODE == 'tc3' else 1)
+  return _abi.spconv_fwd(feat, conv_mod.kernel.detach(), km, out)
+
 
 class RegionType(Enum):
   HYPER_CUBE = 0
@@ -226,6 +250,17 @@ class _ConvBase(nn.Module):
       if self.bias is not None:
         self.bias.uniform_(-stdv, stdv)
 
+  def kernel_transposed(self):
+    """[K, cout, cin] copy of the kernel for the tensor-core path, cached per parameter version."""
+    k = self.kernel
+    ver = (k._version, k.device, k.data_ptr())
+    cache = getattr(self, '_wt_cache', None)
+    if cache is None or cache[0] != ver:
+      wt = _abi.transpose_weight(k.detach().contiguous(), self.kernel_volume, self.in_channels,
+                                 self.out_channels)
+      self._wt_cache = cache = (ver, wt)
+    return cache[1]
+
   def forward(self, x):
     assert isinstance(x, SparseTensor), 'input must be a SparseTensor'
     assert x.D == self.dimension
@@ -246,7 +281,7 @@ class _ConvBase(nn.Module):
       out = _abi.spconv_table_fwd(x.F, w, km, self.out_channels)
     else:
       out = torch.zeros(km.n_out, self.out_channels, dtype=torch.float32, device=x.device)
-      _abi.spconv_fwd(x.F, w, km, out)
+      sparse_conv(x.F, self, km, out)
     if self.bias is not None:
       out = _abi.affine_act(out, residual=None, scale=torch.ones_like(self.bias).reshape(-1),
                             shift=self.bias.detach().reshape(-1).contiguous(), out=out)

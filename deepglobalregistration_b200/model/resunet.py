@@ -129,7 +129,7 @@ class ResUNet2(ME.MinkowskiNetwork):
         and residual is None and not relu:
       return _abi.spconv_table_fwd(feat, w, km, conv_mod.out_channels, scale, shift)
     out = torch.zeros(km.n_out, conv_mod.out_channels, dtype=torch.float32, device=feat.device)
-    _abi.spconv_fwd(feat, w, km, out)
+    ME.sparse_conv(feat, conv_mod, km, out)
     return _abi.affine_act(out, scale=scale, shift=shift, residual=residual, relu=relu, out=out)
 
   def _block_fused(self, feat, block, km):

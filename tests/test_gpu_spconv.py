@@ -64,6 +64,45 @@ def test_spconv_stride1(abi, D, cin, cout, ks):
   _close(out2, so.conv_forward(torch.relu(feat), W, buckets, n), what='spconv_fwd relu_in')
 
 
+@pytest.mark.parametrize('D,cin,cout', [(3, 32, 32), (3, 32, 64), (3, 64, 64), (3, 64, 128), (3, 128, 128),
+                                        (3, 256, 256), (3, 256, 128), (3, 128, 64), (3, 96, 48), (6, 32, 32),
+                                        (6, 256, 256), (3, 32, 16), (3, 64, 240)])
+def test_spconv_tensor_core(abi, D, cin, cout):
+  """tcgen05 path: 3xTF32 must match the fp32 oracle like the FFMA kernel does; single-pass
+  TF32 within 5e-3 of the result's scale."""
+  from deepglobalregistration_b200.me.coords import CoordinateManager, CoordinateMapKey
+  assert abi.tc_supported(cin, cout)
+  coords = _coords(3 * cin + cout + D, 3000, D, 10 if D == 3 else 3)
+  n = len(coords)
+  g = torch.Generator().manual_seed(4)
+  feat = torch.randn(n, cin, generator=g)
+  W = torch.randn(3 ** D, cin, cout, generator=g) / np.sqrt(cin * 8)
+  man = CoordinateManager(torch.from_numpy(coords).cuda())
+  _, km = man.kernel_map(CoordinateMapKey(1), 1, 3)
+  want = so.conv_forward(feat, W, so.kernel_map(coords, coords, so.kernel_offsets(3, D, 1)), n)
+  Wd = W.cuda().contiguous()
+  Wt = abi.transpose_weight(Wd, 3 ** D, cin, cout)
+  assert torch.equal(Wt.cpu(), W.transpose(1, 2).contiguous())
+  out = torch.zeros(n, cout, device='cuda')
+  abi.spconv_tc_fwd(feat.cuda(), Wt, km, out, passes=3)
+  _close(out, want, what='tcgen05 3xTF32')
+  out1 = torch.zeros(n, cout, device='cuda')
+  abi.spconv_tc_fwd(feat.cuda(), Wt, km, out1, passes=1)
+  scale = float(want.abs().max())
+  assert float((out1.cpu() - want).abs().max()) <= 5e-3 * scale, 'tcgen05 1xTF32'
+  # accumulate onto a non-zero initial value, twice in a row (persistent CTAs, phase tracking)
+  init = torch.randn(n, cout, generator=g)
+  out2 = init.clone().cuda()
+  abi.spconv_tc_fwd(feat.cuda(), Wt, km, out2, passes=3)
+  abi.spconv_tc_fwd(feat.cuda(), Wt, km, out2, passes=3)
+  _close(out2, init + 2 * want, what='tcgen05 accumulate')
+
+
+def test_tc_unsupported_shapes_fall_back(abi):
+  assert not abi.tc_supported(1, 32) and not abi.tc_supported(48, 32) and not abi.tc_supported(32, 8)
+  assert not abi.tc_supported(32, 264) and abi.tc_supported(64, 256)
+
+
 @pytest.mark.parametrize('D,cin,cout', [(3, 32, 64), (3, 128, 256), (6, 32, 64)])
 def test_spconv_stride2_and_transpose(abi, D, cin, cout):
   from deepglobalregistration_b200.me.coords import CoordinateManager, CoordinateMapKey
