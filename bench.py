@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py - scan-pairs/sec of DGR's pairwise-registration hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \\
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one full register() of one synthetic 3DMatch-shape scan pair (BASELINE.json
+configs[1]/[3] shape: ~50k voxels per cloud at 0.05 m, FCGF feature dim 32, ResUNetBN2C for
+both networks): voxelise x2 -> FCGF x2 -> feature kNN -> 6-D inlier network -> weights ->
+weighted Procrustes + SE(3) refinement.  ICP / RANSAC (open3d) are outside the built path
+on both arms.  Pairs are independent: each rank registers its own pairs (weak scaling) and
+the poses are all-gathered over NCCL at the end of the timed region.
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with the raw scans resident in HBM;
+`e2e` = pairs/s through DeepGlobalRegistration.register(host ndarrays) including the H2D
+copy of both scans and the D2H read of the pose.  `--impl reference` times the CPU oracle
+port of the same path (MinkowskiEngine cannot be installed offline) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from deepglobalregistration_b200 import synthetic as syn
+
+WORKLOAD = '3dmatch_shape_pair_register'
+N_RAW = 250_000               # raw points per scan -> ~50k voxels at 0.05 m
+SAMPLE_N_RAW = 8_000          # CPU sample: same generator, ~4k voxels per cloud
+SAMPLE_EXTENT = (1.5, 1.2, 1.0)
+VOXEL = 0.05
+POOL = 3                      # distinct pairs per rank, cycled over the steps
+
+
+def log(*a):
+  print(*a, file=sys.stderr, flush=True)
+
+
+def base_config(n_gpus):
+  return {'workload': WORKLOAD, 'n_raw_points_per_scan': N_RAW, 'voxel_size': VOXEL, 'feat_dim': 32,
+          'fcgf_model': 'ResUNetBN2C(D=3,conv1_k=7)', 'inlier_model': 'ResUNetBN2C(D=6,conv1_k=3)',
+          'conv_arithmetic': 'tcgen05 3xTF32 (fp32-accurate) + fp32 FFMA for conv1',
+          'parallelism': f'pair-sharded dp{n_gpus}', 'pairs_per_step_per_gpu': 1,
+          'excluded_on_both_arms': 'open3d ICP / RANSAC safeguard (not built)',
+          'l2_policy': 'inputs larger than L2: every step streams the 944 MB inlier-net weights '
+                       '(L2 = 126 MB) and cycles through %d distinct pairs' % POOL}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+  Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.rows, self.proc = [], None
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
+                                    '--format=csv,noheader,nounits', '-lms', '100'],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception as e:   # noqa: BLE001
+      log('clock sampler unavailable:', e)
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append((time.time(), line.strip()))
+
+  def stop(self, t0, t1):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+    self.proc.terminate()
+    sm, mx, reasons = [], None, set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for ts, line in self.rows:
+      if not (t0 - 0.05 <= ts <= t1 + 0.15):
+        continue
+      f = [x.strip() for x in line.split(',')]
+      try:
+        sm.append(float(f[0]))
+        mx = float(f[1])
+        for nm, v in zip(names, f[3:7]):
+          if v.lower().startswith('active'):
+            reasons.add(nm)
+      except (ValueError, IndexError):
+        continue
+    return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'samples': len(sm),
+            'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) - also the --impl reference arm
+# ------------------------------------------------------------------------------------------
+def effective_cpus():
+  """Host threads this process may really use: affinity mask and cgroup CPU quota, not nproc."""
+  n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+  try:
+    quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+    if quota != 'max':
+      n = min(n, max(1, int(np.ceil(int(quota) / int(period)))))
+  except Exception:   # noqa: BLE001
+    try:
+      q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+      p = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+      if q > 0:
+        n = min(n, max(1, int(np.ceil(q / p))))
+    except Exception:   # noqa: BLE001
+      pass
+  return n
+
+
+CPU_THREADS = None
+
+
+def cpu_threads():
+  """Threads for the CPU arm: all usable cores, capped at 32 (the per-offset mm / index_add
+  of the oracle stop scaling well before that and oversubscription is catastrophic)."""
+  global CPU_THREADS
+  if CPU_THREADS is None:
+    CPU_THREADS = max(1, min(effective_cpus(), 32))
+    torch.set_num_threads(CPU_THREADS)
+  return CPU_THREADS
+
+
+def cpu_sample_time(state, seed, reps=1):
+  """Seconds per pair of the CPU oracle on the bounded sample."""
+  from oracle import pipeline as op
+  cpu_threads()
+  xyz0, xyz1, _ = syn.room_pair(seed, n_raw=SAMPLE_N_RAW, extent=SAMPLE_EXTENT)
+  ts, info = [], {}
+  for _ in range(reps):
+    t = time.perf_counter()
+    _, taps = op.register(state, xyz0, xyz1)
+    ts.append(time.perf_counter() - t)
+    info = {'n0': int(len(taps['coords0'])), 'n1': int(len(taps['coords1'])), 'branch': taps['branch']}
+  return float(np.median(ts)), info
+
+
+def sample_desc(info):
+  return (f'1 pair of the same generator at {SAMPLE_N_RAW} raw points/scan -> N0={info["n0"]}, '
+          f'N1={info["n1"]} voxels (the workload has ~51k/~40k); pairs/s of the SAMPLE, not extrapolated; '
+          'CPU path = oracle port (torch-CPU index_select/mm/index_add per kernel offset, the algorithm '
+          "of MinkowskiEngine's CPU backend) + restated kNN / Procrustes / Adam refinement")
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  state = syn.make_checkpoint(0)
+  cores = cpu_threads()
+  log(f'[bench] reference arm: {cores} threads (nproc {os.cpu_count()}, usable {effective_cpus()})')
+  for i in range(args.warmup):
+    cpu_sample_time(state, 100 + i)
+  t0 = time.perf_counter()
+  info = {}
+  for i in range(args.steps):
+    _, info = cpu_sample_time(state, i)
+  dt = time.perf_counter() - t0
+  val = args.steps / dt
+  cfg = base_config(args.gpus)
+  cfg['reference_arm'] = 'CPU oracle port on a bounded sample per step (MinkowskiEngine is not installable offline)'
+  line = {'impl': 'reference', 'metric': 'scan_pairs_per_sec', 'value': val, 'unit': 'pairs/s',
+          'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+          'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+          'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+                           'sample': sample_desc(info)},
+          'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+  print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+  import torch.distributed as dist
+  from deepglobalregistration_b200 import _abi
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+
+  state = syn.make_checkpoint(0)
+  cfg = types.SimpleNamespace(weights=state, clip_weight_thresh=0.05, verbose=False)
+  dgr = DeepGlobalRegistration(cfg, device=dev)
+
+  # this rank's pairs (seeds disjoint across ranks): host copies for e2e, device copies for `value`
+  pairs_host = [syn.room_pair(1000 * rank + i, n_raw=N_RAW) for i in range(POOL)]
+  pairs_dev = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b, _ in pairs_host]
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def gather_poses(poses):
+    t = torch.from_numpy(np.stack(poses).reshape(len(poses), 16)).float().to(dev)
+    if world > 1:
+      out = [torch.empty_like(t) for _ in range(world)]
+      dist.all_gather(out, t)
+      return torch.stack(out).cpu()
+    return t.cpu()
+
+  def timed(n_steps, host_inputs, profile=False):
+    """K steps bracketed by barrier + synchronize; device time by CUDA events."""
+    barrier()
+    if profile:
+      _abi.CONV_PROFILE = []
+    l0, d0 = _abi.lib().dgr_launch_count(), _abi.D2H_BYTES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    poses = []
+    for s in range(n_steps):
+      a, b = (pairs_host[s % POOL][:2] if host_inputs else pairs_dev[s % POOL])
+      poses.append(dgr.register(a, b))
+    gathered = gather_poses(poses)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - w0
+    ms = e0.elapsed_time(e1)
+    prof, _abi.CONV_PROFILE = _abi.CONV_PROFILE, None
+    launches = _abi.lib().dgr_launch_count() - l0
+    d2h = _abi.D2H_BYTES - d0
+    if world > 1:
+      tm = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+      dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+      ms, wall = float(tm[0]), float(tm[1]) / 1e3
+    return dict(ms=ms, wall=wall, launches=launches, d2h=d2h, prof=prof, poses=gathered)
+
+  log(f'[bench] rank {rank}/{world}: model + {POOL} pairs ready, warming up')
+  # warm-up: every pair of the pool at least max(W, 3) times on both input paths, so that the
+  # caching allocator has seen every buffer size before anything is timed
+  n_warm = max(args.warmup, 3) * POOL
+  timed(n_warm, host_inputs=False)
+  timed(POOL, host_inputs=True)
+  log('[bench] warm-up done, timing')
+
+  sampler = ClockSampler(local) if rank == 0 else None
+  t_start = time.time()
+  res = timed(args.steps, host_inputs=False, profile=True)     # `value`: scans resident in HBM
+  t_mid = time.time()
+  res_e2e = timed(args.steps, host_inputs=True)                 # `e2e`: host buffers in, pose out
+  t_end = time.time()
+  clocks = sampler.stop(t_start, t_end) if sampler else None
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  K = args.steps
+  value = world * K / (res['ms'] / 1e3)
+  e2e = world * K / (res_e2e['ms'] / 1e3)
+
+  # ---- roofline of the dominant kernel (live CUDA events around every launch) ---------------
+  peaks, peak_src = None, 'fallback (B200_PROFILING.md: 6650 GB/s, 1590 TFLOP/s bf16)'
+  try:
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    peak_src = 'measured (MEASURED_PEAKS.json)'
+  except Exception:   # noqa: BLE001
+    pass
+  hbm_peak = float(peaks['hbm_gbs']) if peaks else 6650.0
+  bf16_peak = float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])) if peaks else 1400.0
+  by = {}
+  for name, a, b, flops, nbytes in res['prof']:
+    d = by.setdefault(name, [0, 0.0, 0.0, 0.0])
+    d[0] += 1
+    d[1] += a.elapsed_time(b)
+    d[2] += flops
+    d[3] += nbytes
+  dom = max(by, key=lambda k: by[k][1]) if by else None
+  roofline, roofline_tensor, kernel_share = None, None, None
+  if dom:
+    n, ms, flops, nbytes = by[dom]
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    tfs = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    try:   # per-launch DRAM bytes from the committed ncu --set full capture, if present
+      traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_spconv_tc_traffic.json')))['dram_bytes_per_launch']
+    except Exception:   # noqa: BLE001
+      pass
+    roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
+                'launches_per_step': n / K, 'avg_launch_ms': ms / n,
+                'algorithmic_bytes_per_launch': nbytes / n,
+                'bytes_model': 'SURVEY 8(d) gather-scatter model: P*(Cin+Cout)*4 + 8*P + K_nonempty*Cin*Cout*4'}
+    roofline_tensor = {'kernel': dom, 'bound': 'tensor', 'achieved': tfs, 'peak': bf16_peak, 'unit': 'TFLOP/s',
+                       'frac': tfs / bf16_peak, 'algorithmic_flops_per_launch': flops / n,
+                       'note': 'algorithmic fp32 FLOPs 2*P*Cin*Cout; the kernel spends 3 TF32 MMAs per product '
+                               '(3xTF32) and TF32 runs at half the bf16 rate, so its ceiling is peak/6'}
+    kernel_share = {k: v[1] / (res['ms']) for k, v in by.items()}
+
+  log(f'[bench] value {value:.2f} pairs/s, e2e {e2e:.2f} pairs/s; timing the CPU sample')
+  # ---- CPU baseline on a bounded sample --------------------------------------------------------
+  cpu_s, info = cpu_sample_time(state, 0, reps=1)
+  cpu = {'value': 1.0 / cpu_s, 'unit': 'pairs/s', 'cores': cpu_threads(), 'kind': 'port',
+         'sample': sample_desc(info), 'seconds_per_sample_pair': cpu_s}
+
+  cfg_out = base_config(world)
+  cfg_out.update(n0=dgr.last_info.get('n0'), n1=dgr.last_info.get('n1'), branch=dgr.last_branch,
+                 refine_iterations=dgr.last_info.get('iterations'))
+  h2d = int(sum(a.nbytes + b.nbytes for a, b, _ in pairs_host) / POOL)
+  fixed_d2h = 2 * 8 + 8 + 9 * 4 + 8 + 64     # counts, spec flags, coarse-map sizes, wsum, pose
+  line = {'metric': 'scan_pairs_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K,
+          'warmup': max(args.warmup, 3) * POOL + POOL, 'ms_per_step': res['ms'] / K, 'higher_is_better': True,
+          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
+          'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d,
+                  'd2h_bytes_per_step': int(res_e2e['d2h'] / K) + fixed_d2h,
+                  'ms_per_step': res_e2e['ms'] / K, 'wall_ms_per_step': 1e3 * res_e2e['wall'] / K},
+          'gpu_launches': int(res['launches']), 'gpu_launches_per_step': res['launches'] / K,
+          'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor,
+          'kernel_share_of_step': kernel_share, 'cpu_baseline': cpu,
+          'wall_ms_per_step': 1e3 * res['wall'] / K,
+          'published_reference': '0.69 s/pair without safeguard+ICP (reference assets/results.npz, unknown GPU)'}
+  print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == '__main__':
+  main()

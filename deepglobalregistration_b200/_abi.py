@@ -30,6 +30,7 @@ _p, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_do
 SIGNATURES = {
     'dgr_version': [],
     'dgr_last_error': [],
+    'dgr_launch_count': [],
     'dgr_device_check': [_i32],
     'dgr_quantize_points': [_p, _i32, _i64, _f64, _i32, _p, _p, _p],
     'dgr_coords_minmax': [_p, _i64, _i32, _p, _p],
@@ -59,7 +60,7 @@ SIGNATURES = {
     'dgr_sigmoid_clip_sum': [_p, _i64, _f32, _p, _p, _p],
     'dgr_se3_register': [_p, _p, _p, _p, _i64, _f32, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p],
 }
-_RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
+_RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_launch_count': _i64, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
 
 _lib = None
 
@@ -131,6 +132,24 @@ def next_pow2(n):
 
 
 # --------------------------------------------------------------------------- #
+# scratch arena: the big transient workspaces (dense neighbour tables, scan / pack buffers)
+# are views of per-(device, stream) buffers that only ever grow, so steady-state calls
+# never reach cudaMalloc/cudaFree whatever the cloud sizes are.  Work on one stream is
+# ordered, which is what makes the reuse safe.
+# --------------------------------------------------------------------------- #
+_ARENA = {}
+
+
+def scratch(name, numel, dtype, device):
+  key = (name, dtype, device.index, stream())
+  buf = _ARENA.get(key)
+  if buf is None or buf.numel() < numel:
+    buf = torch.empty(max(int(numel * 1.25), 1024), dtype=dtype, device=device)
+    _ARENA[key] = buf
+  return buf[:numel]
+
+
+# --------------------------------------------------------------------------- #
 # thin typed wrappers (allocate outputs / workspaces with torch, call the ABI)
 # --------------------------------------------------------------------------- #
 class HashTable:
@@ -177,9 +196,9 @@ def unique_first(coords, spec):
   sel = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
   inverse = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
   cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-  slot = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-  rank = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-  scan = torch.empty(lib().dgr_scan_ws_elems(n), dtype=torch.int32, device=dev)
+  slot = scratch('uf_slot', max(n, 1), torch.int32, dev)
+  rank = scratch('uf_rank', max(n, 1), torch.int32, dev)
+  scan = scratch('uf_scan', lib().dgr_scan_ws_elems(n), torch.int32, dev)
   call('dgr_unique_first', ptr(coords), n, ncols, ptr(spec), ptr(table.keys), ptr(table.vals), table.cap,
        ptr(sel), ptr(inverse), ptr(cnt), ptr(slot), ptr(rank), ptr(scan), stream())
   return table, sel, inverse, cnt
@@ -229,13 +248,18 @@ def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
   K = offsets.shape[0]
   km = KernelMap()
   km.K, km.n_in, km.n_out = K, n_in, n_out
-  nbr = torch.empty(K, max(n_out, 1), dtype=torch.int32, device=dev)
+  if keep_table:
+    nbr = torch.empty(K, max(n_out, 1), dtype=torch.int32, device=dev)
+  else:
+    nbr = scratch('km_nbr', K * max(n_out, 1), torch.int32, dev).view(K, max(n_out, 1))
   call('dgr_kernel_map_table', ptr(out_coords), n_out, ncols, ptr(spec), ptr(in_table.keys),
        ptr(in_table.vals), in_table.cap, ptr(offsets), K, ptr(nbr), stream())
-  ws = torch.empty(lib().dgr_kmap_ws_elems(K, n_out), dtype=torch.int32, device=dev)
+  ws = scratch('km_ws', lib().dgr_kmap_ws_elems(K, n_out), torch.int32, dev)
   kofs = torch.empty(K + 1, dtype=torch.int32, device=dev)
   call('dgr_kernel_map_count', ptr(nbr), K, n_out, ptr(ws), ptr(kofs), stream())
   kofs_host = kofs.cpu().numpy()          # the one host read of this map: P and the tile count
+  global D2H_BYTES
+  D2H_BYTES += kofs_host.nbytes
   P = int(kofs_host[K])
   counts = kofs_host[1:] - kofs_host[:-1]
   n_tiles = int(((counts + TILE_ROWS - 1) // TILE_ROWS).sum())
@@ -257,8 +281,9 @@ def spconv_fwd(feat, weight, km, out, relu_in=False):
   cin, cout = feat.shape[1], out.shape[1]
   assert weight.numel() == km.K * cin * cout, (weight.shape, km.K, cin, cout)
   assert feat.shape[0] == km.n_in and out.shape[0] == km.n_out, (feat.shape, out.shape, km.n_in, km.n_out)
-  call('dgr_spconv_fwd', ptr(feat), cin, ptr(weight), cout, ptr(km.in_idx), ptr(km.out_idx), ptr(km.kofs),
-       ptr(km.tile_k), ptr(km.tile_start), km.n_tiles, TILE_ROWS, int(relu_in), ptr(out), stream())
+  _conv_profiled('spconv_fwd_kernel', km, cin, cout, lambda: call(
+      'dgr_spconv_fwd', ptr(feat), cin, ptr(weight), cout, ptr(km.in_idx), ptr(km.out_idx), ptr(km.kofs),
+      ptr(km.tile_k), ptr(km.tile_start), km.n_tiles, TILE_ROWS, int(relu_in), ptr(out), stream()))
   return out
 
 
@@ -274,15 +299,37 @@ def transpose_weight(weight, K, cin, cout):
   return wt
 
 
+# When set to a list, every sparse-convolution launch appends
+# (kernel name, start event, end event, algorithmic flops, gather-scatter-model bytes):
+# bench.py's live per-kernel roofline measurement (CUDA events on the launching stream).
+CONV_PROFILE = None
+D2H_BYTES = 0          # bytes this module has read back to the host (counts, bucket offsets, results)
+
+
+def _conv_profiled(name, km, cin, cout, fn):
+  if CONV_PROFILE is None:
+    return fn()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  fn()
+  e1.record()
+  nonempty = int((km.kofs_host[1:] > km.kofs_host[:-1]).sum())
+  flops = 2.0 * km.n_pairs * cin * cout
+  # gather read + scatter write + (in, out) index pair + weights of non-empty offsets
+  nbytes = km.n_pairs * (cin + cout) * 4.0 + 8.0 * km.n_pairs + nonempty * cin * cout * 4.0
+  CONV_PROFILE.append((name, e0, e1, flops, nbytes))
+
+
 def spconv_tc_fwd(feat, weight_t, km, out, passes=3):
   """Tensor-core gather-GEMM-scatter: out[km.out_idx] += feat[km.in_idx] @ W[kappa]."""
   _chk(feat, torch.float32, 'feat'); _chk(weight_t, torch.float32, 'weight_t'); _chk(out, torch.float32, 'out')
   cin, cout = feat.shape[1], out.shape[1]
   assert weight_t.numel() == km.K * cin * cout
   assert feat.shape[0] == km.n_in and out.shape[0] == km.n_out
-  call('dgr_spconv_tc_fwd', ptr(feat), cin, ptr(weight_t), cout, ptr(km.in_idx), ptr(km.out_idx),
-       ptr(km.kofs), ptr(km.tile_k), ptr(km.tile_start), km.n_tiles, TILE_ROWS, int(passes), ptr(out),
-       stream())
+  _conv_profiled('spconv_tc_kernel', km, cin, cout, lambda: call(
+      'dgr_spconv_tc_fwd', ptr(feat), cin, ptr(weight_t), cout, ptr(km.in_idx), ptr(km.out_idx),
+      ptr(km.kofs), ptr(km.tile_k), ptr(km.tile_start), km.n_tiles, TILE_ROWS, int(passes), ptr(out),
+      stream()))
   return out
 
 
@@ -332,7 +379,7 @@ def l2_normalize(x):
 def knn_top1(f0, f1, return_distance=False):
   _chk(f0, torch.float32, 'f0'); _chk(f1, torch.float32, 'f1')
   n0 = f0.shape[0]
-  ws = torch.empty(max(n0, 1), dtype=torch.int64, device=f0.device)
+  ws = scratch('knn_ws', max(n0, 1), torch.int64, f0.device)
   idx = torch.empty(n0, dtype=torch.int32, device=f0.device)
   dist = torch.empty(n0, dtype=torch.float32, device=f0.device) if return_distance else None
   call('dgr_knn_top1', ptr(f0), n0, ptr(f1), f1.shape[0], f0.shape[1], ptr(ws), ptr(idx), ptr(dist), stream())
@@ -359,7 +406,7 @@ def se3_register(x, y, w, idx1=None, quantization_size=1.0, max_iter=1000, max_b
   """-> device float32 [16]: R (9), t (3), iterations, loss, break_count, n_active."""
   _chk(x, torch.float32, 'x'); _chk(y, torch.float32, 'y'); _chk(w, torch.float32, 'w')
   n = x.shape[0]
-  pack = torch.empty(7 * n, dtype=torch.float32, device=x.device)
+  pack = scratch('se3_pack', 7 * n, torch.float32, x.device)
   cnt = torch.empty(4, dtype=torch.int32, device=x.device)
   res = torch.empty(16, dtype=torch.float32, device=x.device)
   call('dgr_se3_register', ptr(x), ptr(y), ptr(idx1), ptr(w), n, float(quantization_size), int(max_iter),

@@ -2,11 +2,16 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace {
 thread_local char g_error[1024] = "";
+std::atomic<long long> g_launches{0};
 }
+
+void dgr_note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void dgr_set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,6 +23,8 @@ void dgr_set_error(const char* fmt, ...) {
 extern "C" {
 
 int32_t dgr_version(void) { return 100; }   // 0.1.0
+
+int64_t dgr_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 const char* dgr_last_error(void) { return g_error; }
 

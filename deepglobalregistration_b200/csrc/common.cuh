@@ -6,6 +6,7 @@
 #include "dgr_b200.h"
 
 void dgr_set_error(const char* fmt, ...);
+void dgr_note_launches(int n);   // bookkeeping for dgr_launch_count()
 
 #define DGR_CUDA_CHECK(expr)                                                            \
   do {                                                                                  \

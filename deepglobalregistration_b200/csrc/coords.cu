@@ -369,6 +369,7 @@ int32_t dgr_coords_minmax(const int32_t* coords, int64_t n, int32_t ncols, int32
     if (blocks > 1184) blocks = 1184;   // 148 SMs x 8
     minmax_kernel<<<blocks, kThreads, 0, st>>>(coords, n, ncols, minmax);
   }
+  dgr_note_launches(n > 0 ? 2 : 1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -384,6 +385,7 @@ int32_t dgr_quantize_points(const void* xyz, int32_t is_f64, int64_t n, double v
     else
       quantize_kernel<float><<<dgr_blocks(n, kThreads), kThreads, 0, st>>>(
           (const float*)xyz, n, (float)voxel, batch, coords);
+    dgr_note_launches(1);
     DGR_LAUNCH_CHECK();
   }
   return dgr_coords_minmax(coords, n, 4, minmax, stream);
@@ -393,6 +395,7 @@ int32_t dgr_keyspec_build(const int32_t* minmax, int32_t ncols, int32_t margin, 
                           void* stream) {
   DGR_ARG_CHECK(ncols >= 1 && ncols <= DGR_MAX_COLS, "ncols out of range");
   keyspec_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(minmax, ncols, margin, spec);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -400,6 +403,7 @@ int32_t dgr_keyspec_build(const int32_t* minmax, int32_t ncols, int32_t margin, 
 int32_t dgr_hash_clear(uint64_t* keys, int32_t* vals, int64_t cap, void* stream) {
   DGR_ARG_CHECK(cap > 0 && (cap & (cap - 1)) == 0, "capacity must be a power of two");
   hash_clear_kernel<<<dgr_blocks(cap, kThreads), kThreads, 0, (cudaStream_t)stream>>>(keys, vals, cap);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -428,6 +432,7 @@ int32_t dgr_unique_first(const int32_t* coords, int64_t n, int32_t ncols, const 
   unique_scatter_kernel<<<nb, kThreads, 0, st>>>(rank_ws, slot_ws, n, scan_ws, sel, vals);
   inverse_kernel<<<dgr_blocks(n, kThreads), kThreads, 0, st>>>(slot_ws, vals, n, inverse);
   copy_total_kernel<<<1, 1, 0, st>>>(scan_ws + nb, n_unique);
+  dgr_note_launches(7);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -439,6 +444,7 @@ int32_t dgr_hash_find(const int32_t* coords, int64_t n, int32_t ncols, const dgr
   if (n == 0) return DGR_OK;
   hash_find_kernel<<<dgr_blocks(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
       coords, n, ncols, spec, keys, vals, (uint64_t)cap - 1, rows_out);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -448,6 +454,7 @@ int32_t dgr_gather_rows_i32(const int32_t* src, const int32_t* idx, int64_t n, i
   if (n == 0) return DGR_OK;
   gather_rows_kernel<<<dgr_blocks(n * ncols, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
       src, idx, n, ncols, out);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -458,6 +465,7 @@ int32_t dgr_stride_coords(const int32_t* coords, int64_t n, int32_t ncols, int32
   if (n == 0) return DGR_OK;
   stride_coords_kernel<<<dgr_blocks(n * ncols, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
       coords, n, ncols, out_stride, out);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -472,6 +480,7 @@ int32_t dgr_kernel_map_table(const int32_t* out_coords, int64_t n_out, int32_t n
   dim3 grid(dgr_blocks(n_out, kThreads), (K + kKappaChunk - 1) / kKappaChunk);
   kernel_map_table_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
       out_coords, n_out, ncols, spec, in_keys, in_vals, (uint64_t)in_cap - 1, offsets, K, nbr);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -490,6 +499,7 @@ int32_t dgr_kernel_map_count(const int32_t* nbr, int32_t K, int64_t n_out, int32
   block_count_kernel<true><<<dim3(bpk, K), kThreads, 0, st>>>(nbr, n_out, block_ws);
   scan_blocks_kernel<<<1, 1024, 0, st>>>(block_ws, (int64_t)K * bpk);
   kofs_kernel<<<dgr_blocks(K + 1, kThreads), kThreads, 0, st>>>(block_ws, K, (int)bpk, kofs);
+  dgr_note_launches(3);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -499,6 +509,7 @@ int32_t dgr_kernel_map_fill(const int32_t* nbr, int32_t K, int64_t n_out, const 
   const unsigned bpk = dgr_blocks(n_out, kScanElems);
   kernel_map_fill_kernel<<<dim3(bpk, K), kThreads, 0, (cudaStream_t)stream>>>(nbr, n_out, block_ws,
                                                                             in_idx, out_idx);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -509,6 +520,7 @@ int32_t dgr_kernel_map_tiles(const int32_t* kofs, int32_t K, int32_t tile_rows, 
   if (n_tiles == 0) return DGR_OK;
   tiles_kernel<<<1, 1024, (K + 1) * sizeof(int), (cudaStream_t)stream>>>(kofs, K, tile_rows, n_tiles,
                                                                         tile_k, tile_start);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }

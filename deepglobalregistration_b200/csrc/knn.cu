@@ -182,6 +182,7 @@ extern "C" int32_t dgr_knn_top1(const float* f0, int64_t n0, const float* f1, in
       knn_top1_generic_kernel<<<dgr_blocks(n0, 128), 128, 0, st>>>(f0, (int)n0, f1, (int)n1, c, packed);
   }
   knn_unpack_kernel<<<dgr_blocks(n0, kThreads), kThreads, 0, st>>>(packed, n0, idx, dist);
+  dgr_note_launches(3);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }

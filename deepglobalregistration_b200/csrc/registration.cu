@@ -515,6 +515,7 @@ int32_t dgr_inlier_coords(const int32_t* coords0, const int32_t* coords1, const 
   if (n0 == 0) return DGR_OK;
   inlier_coords_kernel<<<dgr_blocks(n0, 256), 256, 0, (cudaStream_t)stream>>>(coords0, coords1, idx1, n0,
                                                                            out);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -527,6 +528,7 @@ int32_t dgr_sigmoid_clip_sum(const float* logit, int64_t n, float clip, float* w
   unsigned blocks = dgr_blocks(n, 256 * 4);
   if (blocks > 592) blocks = 592;
   sigmoid_clip_sum_kernel<<<blocks, 256, 0, st>>>(logit, n, clip, w, wsum);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -547,6 +549,7 @@ int32_t dgr_se3_register(const float* x, const float* y, const int32_t* idx1, co
   se3_register_kernel<<<kClusterSize, kRegThreads, smem, st>>>(pack_ws, n, quantization_size, max_iter,
                                                               max_break_count, break_threshold_ratio,
                                                               lr, gamma, eps, result);
+  dgr_note_launches(2);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }

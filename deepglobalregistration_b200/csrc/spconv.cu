@@ -387,6 +387,7 @@ int32_t dgr_spconv_fwd(const float* in_feat, int32_t cin, const float* weight, i
     else         { if (relu_in) DGR_LAUNCH_SPCONV(64, false, true); else DGR_LAUNCH_SPCONV(64, false, false); }
   }
 #undef DGR_LAUNCH_SPCONV
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -413,6 +414,7 @@ int32_t dgr_spconv_table_fwd(const float* in_feat, int32_t cin, const float* wei
     dgr_set_error("dgr_spconv_table_fwd: cout must be 16, 32 or 64 (got %d)", cout);
     return DGR_ERR_ARG;
   }
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -431,6 +433,7 @@ int32_t dgr_linear_fwd(const float* a, int32_t ca, const float* b, int32_t cb, i
   else
     linear_fwd_kernel<64><<<dim3(tiles, (cout + 63) / 64), kThreads, 0, st>>>(a, ca, b, cb, n, weight, cout,
                                                                             bias, relu, normalize, out);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -447,6 +450,7 @@ int32_t dgr_affine_act(const float* x, int64_t n, int32_t c, const float* scale,
   else
     affine_act_scalar_kernel<<<dgr_blocks(total, kThreads), kThreads, 0, st>>>(x, total, c, scale, shift,
                                                                              residual, relu, out);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -456,6 +460,7 @@ int32_t dgr_cat2(const float* a, int32_t ca, const float* b, int32_t cb, int64_t
   if (n == 0) return DGR_OK;
   cat2_kernel<<<dgr_blocks(n * (ca + cb), kThreads), kThreads, 0, (cudaStream_t)stream>>>(a, ca, b, cb, n,
                                                                                        out);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }
@@ -463,6 +468,7 @@ int32_t dgr_cat2(const float* a, int32_t ca, const float* b, int32_t cb, int64_t
 int32_t dgr_l2_normalize(const float* x, int64_t n, int32_t c, float* out, void* stream) {
   if (n == 0) return DGR_OK;
   l2_normalize_kernel<<<dgr_blocks(n * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(x, n, c, out);
+  dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }

@@ -54,6 +54,8 @@ typedef struct dgr_keyspec {
 /* ---- library ------------------------------------------------------------------------ */
 int32_t dgr_version(void);
 const char* dgr_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+int64_t dgr_launch_count(void);
 /* 0 if device `device` is sm_100 (B200); DGR_ERR_DEVICE otherwise.  Host-only query. */
 int32_t dgr_device_check(int32_t device);
 
