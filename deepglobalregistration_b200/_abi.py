@@ -56,11 +56,14 @@ SIGNATURES = {
     'dgr_cat2': [_p, _i32, _p, _i32, _i64, _p, _p],
     'dgr_l2_normalize': [_p, _i64, _i32, _p, _p],
     'dgr_knn_top1': [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p],
+    'dgr_knn_tc_supported': [_i32],
+    'dgr_knn_tc_ws_elems': [_i64, _i64],
+    'dgr_knn_top1_tc': [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p],
     'dgr_inlier_coords': [_p, _p, _p, _i64, _p, _p],
     'dgr_sigmoid_clip_sum': [_p, _i64, _f32, _p, _p, _p],
     'dgr_se3_register': [_p, _p, _p, _p, _i64, _f32, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p],
 }
-_RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_launch_count': _i64, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
+_RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_knn_tc_ws_elems': _i64, 'dgr_launch_count': _i64, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
 
 _lib = None
 
@@ -376,13 +379,22 @@ def l2_normalize(x):
   return out
 
 
-def knn_top1(f0, f1, return_distance=False):
+KNN_MODE = 'tc'      # 'tc': tensor-core pre-filter + exact candidates; 'simt': fp32 brute force
+
+
+def knn_top1(f0, f1, return_distance=False, mode=None):
+  """Top-1 neighbour of every f0 row in f1 (both modes return identical indices)."""
   _chk(f0, torch.float32, 'f0'); _chk(f1, torch.float32, 'f1')
-  n0 = f0.shape[0]
+  n0, n1, c = f0.shape[0], f1.shape[0], f0.shape[1]
+  mode = mode or KNN_MODE
   ws = scratch('knn_ws', max(n0, 1), torch.int64, f0.device)
   idx = torch.empty(n0, dtype=torch.int32, device=f0.device)
   dist = torch.empty(n0, dtype=torch.float32, device=f0.device) if return_distance else None
-  call('dgr_knn_top1', ptr(f0), n0, ptr(f1), f1.shape[0], f0.shape[1], ptr(ws), ptr(idx), ptr(dist), stream())
+  if mode == 'tc' and lib().dgr_knn_tc_supported(c) and n0 > 0:
+    fws = scratch('knn_fws', lib().dgr_knn_tc_ws_elems(n0, n1), torch.float32, f0.device)
+    call('dgr_knn_top1_tc', ptr(f0), n0, ptr(f1), n1, c, ptr(ws), ptr(fws), ptr(idx), ptr(dist), stream())
+  else:
+    call('dgr_knn_top1', ptr(f0), n0, ptr(f1), n1, c, ptr(ws), ptr(idx), ptr(dist), stream())
   return (idx, dist) if return_distance else idx
 
 

@@ -185,6 +185,15 @@ int32_t dgr_l2_normalize(const float* x, int64_t n, int32_t c, float* out, void*
 int32_t dgr_knn_top1(const float* f0, int64_t n0, const float* f1, int64_t n1, int32_t c,
                      uint64_t* packed_ws, int32_t* idx, float* dist, void* stream);
 
+/* Tensor-core variant for c in {32, 64} (dgr_knn_tc_supported): two tcgen05 (TF32) sweeps
+ * find, per row, the candidate columns whose approximate distance is within a proven error
+ * bound of the row minimum; only those are evaluated with the exact fp32 arithmetic above.
+ * Results are bit-identical to dgr_knn_top1.  ws: dgr_knn_tc_ws_elems(n0, n1) floats. */
+int32_t dgr_knn_tc_supported(int32_t c);
+int64_t dgr_knn_tc_ws_elems(int64_t n0, int64_t n1);
+int32_t dgr_knn_top1_tc(const float* f0, int64_t n0, const float* f1, int64_t n1, int32_t c,
+                        uint64_t* packed_ws, float* ws, int32_t* idx, float* dist, void* stream);
+
 /* ---- correspondences -> 6-D coordinates, weights (core/deep_global_registration.py:261-272) */
 /* out[i] = (coords0[i, 0..3], coords1[idx1[i], 1..3]) int32 [n0, 7]. */
 int32_t dgr_inlier_coords(const int32_t* coords0, const int32_t* coords1, const int32_t* idx1,
