@@ -189,7 +189,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
   import torch.distributed as dist
-  from deepglobalregistration_b200 import _abi
+  from deepglobalregistration_b200 import _abi, sharding
   from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -213,13 +213,9 @@ def run_ours(args):
       dist.barrier()
     torch.cuda.synchronize()
 
-  def gather_poses(poses):
-    t = torch.from_numpy(np.stack(poses).reshape(len(poses), 16)).float().to(dev)
-    if world > 1:
-      out = [torch.empty_like(t) for _ in range(world)]
-      dist.all_gather(out, t)
-      return torch.stack(out).cpu()
-    return t.cpu()
+  def gather_poses(rows):
+    # the path's only collective: one all-gather of [pairs, 20] results (NCCL over NVLink)
+    return sharding.gather_results(rows, world * len(rows), device=dev)
 
   def timed(n_steps, host_inputs, profile=False):
     """K steps bracketed by barrier + synchronize; device time by CUDA events."""
@@ -233,7 +229,9 @@ def run_ours(args):
     poses = []
     for s in range(n_steps):
       a, b = (pairs_host[s % POOL][:2] if host_inputs else pairs_dev[s % POOL])
-      poses.append(dgr.register(a, b))
+      T = dgr.register(a, b)
+      poses.append(sharding.pack_result(T, dgr.last_info.get('wsum', 0.0), dgr.last_info.get('iterations', 0),
+                                        dgr.last_branch))
     gathered = gather_poses(poses)
     e1.record()
     barrier()
