@@ -48,7 +48,7 @@ SIGNATURES = {
     'dgr_kernel_map_tiles': [_p, _i32, _i32, _i32, _p, _p, _p],
     'dgr_spconv_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
     'dgr_spconv_tc_supported': [_i32, _i32],
-    'dgr_transpose_weight': [_p, _i32, _i32, _i32, _p, _p],
+    'dgr_pack_weight_tf32': [_p, _i32, _i32, _i32, _p, _p],
     'dgr_spconv_tc_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
     'dgr_spconv_table_fwd': [_p, _i32, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p],
     'dgr_linear_fwd': [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _i32, _i32, _p, _p],
@@ -294,12 +294,13 @@ def tc_supported(cin, cout):
   return bool(lib().dgr_spconv_tc_supported(int(cin), int(cout)))
 
 
-def transpose_weight(weight, K, cin, cout):
-  """[K, cin, cout] -> [K, cout, cin] (the K-major B operand of the tensor-core path)."""
+def pack_weight_tf32(weight, K, cin, cout):
+  """[K, cin, cout] -> packed TF32 hi/lo slabs [K, cin/32, 2, cout, 32] (shared-memory image
+  order) for the tensor-core convolution."""
   _chk(weight, torch.float32, 'weight')
-  wt = torch.empty(K, cout, cin, dtype=torch.float32, device=weight.device)
-  call('dgr_transpose_weight', ptr(weight), K, cin, cout, ptr(wt), stream())
-  return wt
+  packed = torch.empty(K, cin // 32, 2, cout, 32, dtype=torch.float32, device=weight.device)
+  call('dgr_pack_weight_tf32', ptr(weight), K, cin, cout, ptr(packed), stream())
+  return packed
 
 
 # When set to a list, every sparse-convolution launch appends
@@ -327,7 +328,7 @@ def spconv_tc_fwd(feat, weight_t, km, out, passes=3):
   """Tensor-core gather-GEMM-scatter: out[km.out_idx] += feat[km.in_idx] @ W[kappa]."""
   _chk(feat, torch.float32, 'feat'); _chk(weight_t, torch.float32, 'weight_t'); _chk(out, torch.float32, 'out')
   cin, cout = feat.shape[1], out.shape[1]
-  assert weight_t.numel() == km.K * cin * cout
+  assert weight_t.numel() == 2 * km.K * cin * cout
   assert feat.shape[0] == km.n_in and out.shape[0] == km.n_out
   _conv_profiled('spconv_tc_kernel', km, cin, cout, lambda: call(
       'dgr_spconv_tc_fwd', ptr(feat), cin, ptr(weight_t), cout, ptr(km.in_idx), ptr(km.out_idx),

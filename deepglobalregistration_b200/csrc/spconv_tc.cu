@@ -6,10 +6,10 @@
 //
 //   * one work item = one 128-pair tile of one kernel offset, M = 128 rows (pairs),
 //     N = cout (16..256), K = cin in chunks of 32 floats (one 128-byte swizzle row);
-//   * 8 loader warps gather the 128 input rows (coalesced 16-byte pieces, 8 lanes per row),
-//     and stream the [cout x 32] slab of the offset's weight matrix, split every fp32 value
-//     into a TF32 "hi" part and a TF32 "lo" residual in registers, and store both into
-//     shared memory in the canonical K-major SWIZZLE_128B layout;
+//   * 8 loader warps gather the 128 input rows (coalesced 16-byte pieces, 8 lanes per row,
+//     prefetched one chunk ahead), split every fp32 value into a TF32 "hi" part and an fp32
+//     "lo" residual in registers, and store both into shared memory in the canonical K-major
+//     SWIZZLE_128B layout; one elected thread bulk-copies the weight slab of the stage;
 //   * one elected thread of the MMA warp issues, per 8-wide k-step, the three products
 //     hi*hi + lo*hi + hi*lo (3xTF32: fp32-accurate to ~2^-21 relative) into TMEM;
 //     tcgen05.commit on an mbarrier frees the shared-memory stage / publishes the tile;
@@ -17,9 +17,11 @@
 //     32(w%4).. = pairs 32(w%4)..) and scatter-add rows with red.global.add.v4.f32; two
 //     accumulators in TMEM let the epilogue of tile t overlap the MMAs of tile t+1.
 //
-// CTAs are persistent (grid = resident CTAs); stages are mbarrier-pipelined so the gather
-// of chunk c+1 overlaps the MMAs of chunk c.  Weights are expected TRANSPOSED per offset,
-// [K, cout, cin] (K-major B operand); the host caches that layout per layer.
+// CTAs are persistent (one per SM); stages are mbarrier-pipelined so the gather of chunk c+1
+// overlaps the MMAs of chunk c.  Weights come PRE-SPLIT and PRE-SWIZZLED (dgr_pack_weight_tf32,
+// cached per layer by the host): per (offset, 32-channel chunk) one contiguous slab holding the
+// TF32 hi tile and the lo tile in shared-memory image order, streamed by a single
+// cp.async.bulk (TMA engine) per stage - the loader threads only touch the gathered rows.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -36,16 +38,26 @@ constexpr int kTileM = 128;
 constexpr int kChunk = 32;               // floats of K per stage (128 bytes)
 constexpr int kATileBytes = kTileM * 128;
 
-// split one float4 into tf32 hi / lo and store both at the swizzled 16-byte slot
-__device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, unsigned char* lo_tile, int row,
-                                            int piece) {
+// split one float4 into a TF32 "hi" part (round to nearest) and the exact fp32 residual "lo"
+// (the tensor core truncates lo to TF32: 2^-21 relative overall) and store both 16-byte pieces
+__device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, unsigned char* lo_tile,
+                                            uint32_t off) {
   float4 h, l;
   h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-  l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y);
-  l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
-  const int off = row * 128 + ((piece ^ (row & 7)) << 4);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
   *reinterpret_cast<float4*>(hi_tile + off) = h;
   *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine), completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 
 struct TcShared {
@@ -54,7 +66,6 @@ struct TcShared {
   unsigned long long acc_full[2];
   unsigned long long acc_empty[2];
   uint32_t tmem_base;
-  int s_in[kTileM];
 };
 
 // Warp-specialised persistent kernel.  Roles iterate the same tile sequence
@@ -104,52 +115,63 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
 
   if (warp < kLoaderWarps) {
     // ================================ loaders ============================================
+    // B (weights): one elected thread streams the pre-split, pre-swizzled [hi | lo] slab of
+    // (kappa, chunk) with a single bulk copy that lands on full[s] (complete_tx).
+    // A (features): every thread gathers 4 x 16 B, software-pipelined one chunk ahead.
     const int piece = t & 7, rgrp = t >> 3;   // 8 lanes cover one 128-byte row; 32 row groups
-    const int b_rows_per_thread = (cout + 31) / 32;
+    const uint32_t a_off = (uint32_t)(rgrp * 128 + ((piece ^ (rgrp & 7)) << 4));   // + i * 4096
+    const uint32_t slab_bytes = 2u * (uint32_t)b_tile_bytes;
+    auto load_rows = [&](int tile_id, int (&src)[4]) {
+      const int kap = tile_k[tile_id];
+      const int q0 = tile_start[tile_id];
+      const int nrows = min(kTileM, kofs[kap + 1] - q0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 32 + rgrp;
+        src[i] = (r < nrows) ? __ldg(in_idx + q0 + r) : -1;
+      }
+    };
+    auto load_a = [&](const int (&src)[4], int c, float4 (&v)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        v[i] = src[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)src[i] * cin + c * kChunk +
+                                                                    piece * 4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
     uint32_t it = 0;
+    int src[4], nsrc[4];
+    float4 a_cur[4], a_nxt[4];
+    load_rows(blockIdx.x, src);
+    load_a(src, 0, a_cur);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int kappa = tile_k[tile];
-      const int p0 = tile_start[tile];
-      const int rows = min(kTileM, kofs[kappa + 1] - p0);
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone is done with the previous s_in
-      if (t < kTileM) sh.s_in[t] = (t < rows) ? in_idx[p0 + t] : -1;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      int src_row[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) src_row[i] = sh.s_in[i * 32 + rgrp];
-      const float* wk = wt + (size_t)kappa * cout * cin;
+      const int next_tile = tile + gridDim.x;
+      const bool has_next = next_tile < n_tiles;
+      if (has_next) load_rows(next_tile, nsrc);
+      const float* slab = wt + (size_t)kappa * n_chunks * (slab_bytes / 4);
       for (int c = 0; c < n_chunks; ++c, ++it) {
         const int s = it % n_stages;
         const uint32_t ph = (it / n_stages) & 1;
-        const int c0 = c * kChunk + piece * 4;
-        // issue every global load of this chunk before touching any of them
-        float4 av[4], bv[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          av[i] = src_row[i] >= 0
-                      ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)src_row[i] * cin + c0))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 32 + rgrp;
-          if (i < b_rows_per_thread && r < cout)
-            bv[i] = __ldg(reinterpret_cast<const float4*>(wk + (size_t)r * cin + c0));
-        }
+        // prefetch the next chunk's rows (same tile, or chunk 0 of this CTA's next tile)
+        if (c + 1 < n_chunks) load_a(src, c + 1, a_nxt);
+        else if (has_next) load_a(nsrc, 0, a_nxt);
         mbar_wait(smem_u32(&sh.empty[s]), ph ^ 1);
         unsigned char* a_hi = stage0 + (size_t)s * stage_bytes;
         unsigned char* a_lo = a_hi + kATileBytes;
-        unsigned char* b_hi = a_lo + kATileBytes;
-        unsigned char* b_lo = b_hi + b_tile_bytes;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) split_store(av[i], a_hi, a_lo, i * 32 + rgrp, piece);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 32 + rgrp;
-          if (i < b_rows_per_thread && r < cout) split_store(bv[i], b_hi, b_lo, r, piece);
+        if (t == 0) {
+          mbar_expect_tx(smem_u32(&sh.full[s]), slab_bytes);
+          bulk_g2s(smem_u32(a_lo + kATileBytes), slab + (size_t)c * (slab_bytes / 4), slab_bytes,
+                   smem_u32(&sh.full[s]));
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_store(a_cur[i], a_hi, a_lo, a_off + i * 4096);
         fence_proxy_async();
         mbar_arrive(smem_u32(&sh.full[s]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a_cur[i] = a_nxt[i];
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) src[i] = nsrc[i];
     }
   } else if (warp == kMmaWarp) {
     // ================================ MMA issuer =========================================
@@ -239,28 +261,41 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
   }
 }
 
-// [K, cin, cout] -> [K, cout, cin]
-__global__ void transpose_weight_kernel(const float* __restrict__ w, int cin, int cout, float* __restrict__ wt) {
-  __shared__ float tile[32][33];
-  const size_t base = (size_t)blockIdx.z * cin * cout;
-  int ci = blockIdx.y * 32 + threadIdx.y, co = blockIdx.x * 32 + threadIdx.x;
-  if (ci < cin && co < cout) tile[threadIdx.y][threadIdx.x] = w[base + (size_t)ci * cout + co];
-  __syncthreads();
-  co = blockIdx.x * 32 + threadIdx.y;
-  ci = blockIdx.y * 32 + threadIdx.x;
-  if (ci < cin && co < cout) wt[base + (size_t)co * cin + ci] = tile[threadIdx.x][threadIdx.y];
+// W[K, cin, cout] fp32  ->  packed[K][cin/32][2][cout][32]: for every (kappa, 32-channel chunk) the
+// K-major SWIZZLE_128B shared-memory image of the B operand, TF32 "hi" tile followed by the "lo"
+// residual tile - exactly what one bulk copy drops into a pipeline stage.
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cin, int cout, float* __restrict__ packed) {
+  const int n_chunks = cin / kChunk;
+  const int64_t total = (int64_t)n_chunks * cout * 8;          // 16-byte pieces per kappa
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int kappa = blockIdx.y;
+  const int n = (int)(e % cout);                                 // output channel = B row (fastest: coalesced)
+  const int q = (int)((e / cout) % 8);                           // 16-byte piece inside the 128-byte row
+  const int ch = (int)(e / ((int64_t)cout * 8));
+  const float* src = w + ((size_t)kappa * cin + ch * kChunk + q * 4) * cout + n;
+  float4 v = make_float4(src[0], src[cout], src[2 * (size_t)cout], src[3 * (size_t)cout]);
+  float4 h, l;
+  h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+  float* slab = packed + ((size_t)kappa * n_chunks + ch) * 2 * cout * 32;
+  const int off = n * 32 + ((q ^ (n & 7)) << 2);                 // floats
+  *reinterpret_cast<float4*>(slab + off) = h;
+  *reinterpret_cast<float4*>(slab + (size_t)cout * 32 + off) = l;
 }
 
 }  // namespace
 
 extern "C" {
 
-// Layout transform the tensor-core path needs once per layer: W[K, cin, cout] -> Wt[K, cout, cin].
-int32_t dgr_transpose_weight(const float* w, int32_t K, int32_t cin, int32_t cout, float* wt, void* stream) {
-  DGR_ARG_CHECK(K >= 1 && cin >= 1 && cout >= 1, "bad weight shape");
+// Layout transform the tensor-core path needs once per layer: W[K, cin, cout] ->
+// packed[K][cin/32][2][cout][32] (TF32 hi / lo tiles in shared-memory image order), 2x the size.
+int32_t dgr_pack_weight_tf32(const float* w, int32_t K, int32_t cin, int32_t cout, float* packed, void* stream) {
+  DGR_ARG_CHECK(K >= 1 && cin >= 32 && cin % 32 == 0 && cout >= 8 && cout % 8 == 0, "bad weight shape");
   DGR_ARG_CHECK(K <= 65535, "K too large");
-  dim3 grid((cout + 31) / 32, (cin + 31) / 32, K);
-  transpose_weight_kernel<<<grid, dim3(32, 32), 0, (cudaStream_t)stream>>>(w, cin, cout, wt);
+  const int64_t per_k = (int64_t)(cin / kChunk) * cout * 8;
+  dim3 grid(dgr_blocks(per_k, 256), K);
+  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, cin, cout, packed);
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
@@ -271,7 +306,7 @@ int32_t dgr_spconv_tc_supported(int32_t cin, int32_t cout) {
   return (cin >= 32 && cin % 32 == 0 && cout >= 16 && cout <= 256 && cout % 16 == 0) ? 1 : 0;
 }
 
-// Tensor-core variant of dgr_spconv_fwd.  weight_t is [K, cout, cin] (dgr_transpose_weight).
+// Tensor-core variant of dgr_spconv_fwd.  weight_t is the packed layout of dgr_pack_weight_tf32.
 // passes = 3: 3xTF32 (fp32-accurate, default); passes = 1: single TF32 product (~1e-3 rel.).
 int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight_t, int32_t cout,
                           const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,

@@ -251,12 +251,13 @@ class _ConvBase(nn.Module):
         self.bias.uniform_(-stdv, stdv)
 
   def kernel_transposed(self):
-    """[K, cout, cin] copy of the kernel for the tensor-core path, cached per parameter version."""
+    """Packed TF32 hi/lo copy of the kernel for the tensor-core path (dgr_pack_weight_tf32),
+    cached per parameter version."""
     k = self.kernel
     ver = (k._version, k.device, k.data_ptr())
     cache = getattr(self, '_wt_cache', None)
     if cache is None or cache[0] != ver:
-      wt = _abi.transpose_weight(k.detach().contiguous(), self.kernel_volume, self.in_channels,
+      wt = _abi.pack_weight_tf32(k.detach().contiguous(), self.kernel_volume, self.in_channels,
                                  self.out_channels)
       self._wt_cache = cache = (ver, wt)
     return cache[1]

@@ -141,12 +141,14 @@ int32_t dgr_spconv_fwd(const float* in_feat, int32_t cin, const float* weight, i
                        int32_t tile_rows, int32_t relu_in, float* out, void* stream);
 /* Tensor-core (tcgen05.mma kind::tf32, TMEM accumulator) variant of dgr_spconv_fwd for
  * cin % 32 == 0 and cout in {16, 32, ..., 256} (dgr_spconv_tc_supported returns 1).
- * weight_t is the layer's weight TRANSPOSED per offset to [K, cout, cin]
- * (dgr_transpose_weight; the host caches it per layer).  passes = 3 evaluates every
+ * weight_t is the layer's weight in the packed layout of dgr_pack_weight_tf32
+ * ([K][cin/32][2][cout][32]: per offset and 32-channel chunk the TF32 hi tile and the lo
+ * residual tile in shared-memory image order; the host caches it per layer; 2 * K * cin * cout
+ * floats).  passes = 3 evaluates every
  * product as hi*hi + lo*hi + hi*lo on TF32 splits (fp32-accurate); passes = 1 is plain
  * TF32 (~1e-3 relative), offered as an opt-in fast mode. */
 int32_t dgr_spconv_tc_supported(int32_t cin, int32_t cout);
-int32_t dgr_transpose_weight(const float* w, int32_t K, int32_t cin, int32_t cout, float* wt, void* stream);
+int32_t dgr_pack_weight_tf32(const float* w, int32_t K, int32_t cin, int32_t cout, float* packed, void* stream);
 int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight_t, int32_t cout,
                           const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,
                           const int32_t* tile_k, const int32_t* tile_start, int32_t n_tiles,

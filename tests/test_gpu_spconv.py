@@ -81,8 +81,18 @@ def test_spconv_tensor_core(abi, D, cin, cout):
   _, km = man.kernel_map(CoordinateMapKey(1), 1, 3)
   want = so.conv_forward(feat, W, so.kernel_map(coords, coords, so.kernel_offsets(3, D, 1)), n)
   Wd = W.cuda().contiguous()
-  Wt = abi.transpose_weight(Wd, 3 ** D, cin, cout)
-  assert torch.equal(Wt.cpu(), W.transpose(1, 2).contiguous())
+  Wt = abi.pack_weight_tf32(Wd, 3 ** D, cin, cout)
+  # packed layout: [K, cin/32, (hi, lo), cout, 32] with 16-byte pieces XOR-swizzled by (row & 7)
+  pk = Wt.cpu()
+  hi = pk[:, :, 0] + pk[:, :, 1]                       # hi + lo == the fp32 weight, exactly
+  n_idx = torch.arange(cout)
+  unsw = torch.empty_like(hi)
+  for q in range(8):
+    src_piece = (q ^ (n_idx & 7))
+    for nn in range(cout):
+      unsw[:, :, nn, 4 * q:4 * q + 4] = hi[:, :, nn, 4 * int(src_piece[nn]):4 * int(src_piece[nn]) + 4]
+  want_w = W.reshape(3 ** D, cin // 32, 32, cout).permute(0, 1, 3, 2)
+  assert torch.equal(unsw, want_w)
   out = torch.zeros(n, cout, device='cuda')
   abi.spconv_tc_fwd(feat.cuda(), Wt, km, out, passes=3)
   _close(out, want, what='tcgen05 3xTF32')
