@@ -90,7 +90,7 @@ class DeepGlobalRegistration:
     view.numpy()[...] = xyz
     return view.to(self.device, non_blocking=True)
 
-  def preprocess(self, pcd, _slot=0):
+  def preprocess(self, pcd, _slot=0, _batch=0):
     """Stage 0: voxelise.  -> (xyz float32 [N,3], coords int32 [N,4], feats [N,1]).
     One GPU pass replaces sparse_quantize + the re-flooring of the reference (:134-161):
     floor(xyz / voxel) in the input dtype, first point per voxel, ascending indices."""
@@ -108,7 +108,7 @@ class DeepGlobalRegistration:
         dxyz = dxyz.double()
     else:
       dxyz = self._upload(xyz, _slot)
-    raw_coords, minmax = _abi.quantize_points(dxyz, self.voxel_size)
+    raw_coords, minmax = _abi.quantize_points(dxyz, self.voxel_size, batch=_batch)
     spec = _abi.keyspec_build(minmax, 4, KEY_MARGIN)
     table, sel, _, cnt = _abi.unique_first(raw_coords, spec)
     npts = int(cnt.item())
@@ -126,6 +126,16 @@ class DeepGlobalRegistration:
     """Step 1: FCGF feature per voxel."""
     sinput = SparseTensor(feats, coordinates=coords, device=self.device)
     return self.fcgf_model.forward_fused(sinput).F
+
+  def fcgf_feature_extraction_pair(self, coords0, coords1):
+    """Both clouds of a pair in ONE sparse tensor (batch indices 0 / 1): the hash keys carry the
+    batch column, so neighbourhoods never cross clouds and the features equal two separate
+    forward passes - at half the launches and host synchronisations."""
+    n0 = coords0.shape[0]
+    coords = torch.cat((coords0, coords1), 0)
+    feats = torch.ones(coords.shape[0], 1, device=self.device)
+    F = self.fcgf_model.forward_fused(SparseTensor(feats, coordinates=coords, device=self.device)).F
+    return F[:n0], F[n0:]
 
   def fcgf_feature_matching(self, feats0, feats1):
     """Step 2: nearest neighbour of every feats0 row in feats1."""
@@ -163,12 +173,11 @@ class DeepGlobalRegistration:
     """Main algorithm.  -> 4x4 float64 ndarray mapping cloud 0 into cloud 1's frame."""
     self.reg_timer.tic()
     with torch.no_grad():
-      xyz0, coords0, feats0 = self.preprocess(xyz0, 0)
-      xyz1, coords1, feats1 = self.preprocess(xyz1, 1)
+      xyz0, coords0, feats0 = self.preprocess(xyz0, 0, _batch=0)
+      xyz1, coords1, feats1 = self.preprocess(xyz1, 1, _batch=1)
 
       self.feat_timer.tic()
-      fcgf_feats0 = self.fcgf_feature_extraction(feats0, coords0)
-      fcgf_feats1 = self.fcgf_feature_extraction(feats1, coords1)
+      fcgf_feats0, fcgf_feats1 = self.fcgf_feature_extraction_pair(coords0, coords1)
       self.feat_timer.toc()
 
       idx1 = _abi.knn_top1(fcgf_feats0, fcgf_feats1)              # int32 [N0]

@@ -121,52 +121,82 @@ class ResUNet2(ME.MinkowskiNetwork):
     return out
 
   # ---------------------------------------------------------------------------------------
-  def _conv_bn(self, feat, conv_mod, norm_mod, km, residual=None, relu=False):
-    """sparse conv -> (BN scale/shift [+ residual] [+ ReLU]) in one elementwise pass."""
+  def _conv_bn(self, feat, conv_mod, norm_mod, km, out, residual=None, relu=False):
+    """sparse conv -> (BN scale/shift [+ residual] [+ ReLU]) in one elementwise pass.
+    `out` is a pre-zeroed [n_out, cout] buffer (or None for the output-stationary conv1)."""
     scale, shift = norm_mod.folded()
-    w = conv_mod.kernel.detach()
-    if km.nbr is not None and conv_mod.in_channels <= 8 and conv_mod.out_channels in (16, 32, 64) \
-        and residual is None and not relu:
-      return _abi.spconv_table_fwd(feat, w, km, conv_mod.out_channels, scale, shift)
-    out = torch.zeros(km.n_out, conv_mod.out_channels, dtype=torch.float32, device=feat.device)
+    if out is None:
+      return _abi.spconv_table_fwd(feat, conv_mod.kernel.detach(), km, conv_mod.out_channels, scale, shift)
     ME.sparse_conv(feat, conv_mod, km, out)
     return _abi.affine_act(out, scale=scale, shift=shift, residual=residual, relu=relu, out=out)
 
-  def _block_fused(self, feat, block, km):
-    h = self._conv_bn(feat, block.conv1, block.norm1, km, relu=True)
-    return self._conv_bn(h, block.conv2, block.norm2, km, residual=feat, relu=True)
+  def _uses_table(self, conv_mod, km):
+    return km.nbr is not None and conv_mod.in_channels <= 8 and conv_mod.out_channels in (16, 32, 64)
 
-  def forward_fused(self, x):
-    """Same graph, fused epilogues.  The ReLUs after each block are idempotent (the block
-    already ends in ReLU) and are dropped."""
-    man = x.coordinate_manager
-    key = x.coordinate_map_key
-    feat = x.F
-    skips = {}
+  def _plan(self, man, key):
+    """All coordinate maps and kernel maps of the network, built up front: this is where every
+    host synchronisation of the forward pass happens (one bucket-offset read per map); the
+    convolution phase that follows is launch-only.  Returns the layers in execution order as
+    (conv module, norm module, kernel map, role) with the total size of their outputs."""
+    layers = []
     for l in (1, 2, 3, 4):
       cm = getattr(self, f'conv{l}')
       key_out, km = man.kernel_map(key, cm.stride, cm.kernel_size)
-      feat = self._conv_bn(feat, cm, getattr(self, f'norm{l}'), km)
+      layers.append((cm, getattr(self, f'norm{l}'), km, 'conv'))
       _, km3 = man.kernel_map(key_out, 1, 3)
-      feat = self._block_fused(feat, getattr(self, f'block{l}'), km3)
-      skips[l] = feat
+      blk = getattr(self, f'block{l}')
+      layers += [(blk.conv1, blk.norm1, km3, 'b1'), (blk.conv2, blk.norm2, km3, 'b2')]
       key = key_out
-    up = None
     for l in (4, 3, 2):
       cm = getattr(self, f'conv{l}_tr')
       key_out, km = man.transpose_kernel_map(key, cm.stride, cm.kernel_size)
-      src = feat if up is None else up
-      feat = self._conv_bn(src, cm, getattr(self, f'norm{l}_tr'), km)
+      layers.append((cm, getattr(self, f'norm{l}_tr'), km, 'conv'))
       _, km3 = man.kernel_map(key_out, 1, 3)
-      feat = self._block_fused(feat, getattr(self, f'block{l}_tr'), km3)
+      blk = getattr(self, f'block{l}_tr')
+      layers += [(blk.conv1, blk.norm1, km3, 'b1'), (blk.conv2, blk.norm2, km3, 'b2')]
       key = key_out
-      if l > 2:
-        up = _abi.cat2(feat, skips[l - 1])      # feeds a 3^D transposed conv: materialise the concat
+    total = sum(km.n_out * cm.out_channels for cm, _, km, _ in layers if not self._uses_table(cm, km))
+    return layers, total, key
+
+  def forward_fused(self, x):
+    """Same graph, fused epilogues.  The ReLUs after each block are idempotent (the block
+    already ends in ReLU) and are dropped.  Phase 1 builds every kernel map (all host syncs);
+    phase 2 zero-fills ONE slab holding every convolution output and launches the layers
+    back to back."""
+    man = x.coordinate_manager
+    layers, total, key_final = self._plan(man, x.coordinate_map_key)
+    slab = _abi.scratch(('conv_out', id(self)), max(total, 1), torch.float32, x.device)
+    slab.zero_()
+    ofs = 0
+
+    def take(cm, km):
+      nonlocal ofs
+      if self._uses_table(cm, km):
+        return None
+      n = km.n_out * cm.out_channels
+      buf = slab[ofs:ofs + n].view(km.n_out, cm.out_channels)
+      ofs += n
+      return buf
+
+    feat, skips, block_in, level = x.F, [], None, 0
+    it = iter(layers)
+    for stage in range(7):          # 4 encoder levels, then 3 decoder levels
+      cm, nm, km, _ = next(it)
+      feat = self._conv_bn(feat, cm, nm, km, take(cm, km))
+      c1, n1, km3, _ = next(it)
+      c2, n2, _, _ = next(it)
+      h = self._conv_bn(feat, c1, n1, km3, take(c1, km3), relu=True)
+      feat = self._conv_bn(h, c2, n2, km3, take(c2, km3), residual=feat, relu=True)
+      if stage < 4:
+        skips.append(feat)            # out_s1, out_s2, out_s4, out_s8
+      elif stage < 6:
+        # decoder levels 4 and 3 feed a 3^D transposed conv: materialise ME.cat(decoder, skip)
+        feat = _abi.cat2(feat, skips[2 - (stage - 4)])
     # conv1_tr reads (decoder, skip) directly: ME.cat fused into the 1x1 convolution
-    h = _abi.linear_fwd(feat, self.conv1_tr.kernel.detach(), None, b=skips[1], relu=True)
+    h = _abi.linear_fwd(feat, self.conv1_tr.kernel.detach(), None, b=skips[0], relu=True)
     out = _abi.linear_fwd(h, self.final.kernel.detach(), self.final.bias.detach().reshape(-1).contiguous(),
                           normalize=bool(self.normalize_feature))
-    return ME.SparseTensor(out, coordinate_map_key=key, coordinate_manager=man)
+    return ME.SparseTensor(out, coordinate_map_key=key_final, coordinate_manager=man)
 
 
 class ResUNetBN2(ResUNet2):
