@@ -69,7 +69,7 @@ class ClockSampler:
     self.rows, self.proc = [], None
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
-                                    '--format=csv,noheader,nounits', '-lms', '100'],
+                                    '--format=csv,noheader,nounits', '-lms', '200'],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
@@ -226,12 +226,15 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     e0.record()
-    poses = []
+    poses, marks = [], []
     for s in range(n_steps):
       a, b = (pairs_host[s % POOL][:2] if host_inputs else pairs_dev[s % POOL])
       T = dgr.register(a, b)
       poses.append(sharding.pack_result(T, dgr.last_info.get('wsum', 0.0), dgr.last_info.get('iterations', 0),
                                         dgr.last_branch))
+      ev = torch.cuda.Event(enable_timing=True)
+      ev.record()
+      marks.append(ev)
     gathered = gather_poses(poses)
     e1.record()
     barrier()
@@ -244,8 +247,11 @@ def run_ours(args):
       tm = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
       dist.all_reduce(tm, op=dist.ReduceOp.MAX)
       ms, wall = float(tm[0]), float(tm[1]) / 1e3
-    return dict(ms=ms, wall=wall, launches=launches, d2h=d2h, prof=prof, poses=gathered)
+    steps_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    return dict(ms=ms, wall=wall, launches=launches, d2h=d2h, prof=prof, poses=gathered, steps_ms=steps_ms)
 
+  # started before the warm-up: nvidia-smi's own start-up (NVML init) must not land in the timed region
+  sampler = ClockSampler(local) if rank == 0 else None
   log(f'[bench] rank {rank}/{world}: model + {POOL} pairs ready, warming up')
   # warm-up: every pair of the pool at least max(W, 3) times on both input paths, so that the
   # caching allocator has seen every buffer size before anything is timed
@@ -254,7 +260,6 @@ def run_ours(args):
   timed(POOL, host_inputs=True)
   log('[bench] warm-up done, timing')
 
-  sampler = ClockSampler(local) if rank == 0 else None
   t_start = time.time()
   res = timed(args.steps, host_inputs=False, profile=True)     # `value`: scans resident in HBM
   t_mid = time.time()
@@ -330,6 +335,10 @@ def run_ours(args):
           'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor,
           'kernel_share_of_step': kernel_share, 'cpu_baseline': cpu,
           'wall_ms_per_step': 1e3 * res['wall'] / K,
+          'step_ms': {'min': min(res['steps_ms']), 'median': float(np.median(res['steps_ms'])),
+                      'max': max(res['steps_ms'])},
+          'e2e_step_ms': {'min': min(res_e2e['steps_ms']), 'median': float(np.median(res_e2e['steps_ms'])),
+                          'max': max(res_e2e['steps_ms'])},
           'published_reference': '0.69 s/pair without safeguard+ICP (reference assets/results.npz, unknown GPU)'}
   print(json.dumps(line), flush=True)
   if world > 1:

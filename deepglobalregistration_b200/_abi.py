@@ -43,7 +43,7 @@ SIGNATURES = {
     'dgr_stride_coords': [_p, _i64, _i32, _i32, _p, _p],
     'dgr_kernel_map_table': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _i32, _p, _p],
     'dgr_kmap_ws_elems': [_i32, _i64],
-    'dgr_kernel_map_count': [_p, _i32, _i64, _p, _p, _p],
+    'dgr_kernel_map_count': [_p, _i32, _i64, _p, _p, _p, _p],
     'dgr_kernel_map_fill': [_p, _i32, _i64, _p, _p, _p, _p],
     'dgr_kernel_map_tiles': [_p, _i32, _i32, _i32, _p, _p, _p],
     'dgr_spconv_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
@@ -93,8 +93,16 @@ def _check(status, name):
     raise DgrError(f'{name} failed ({status}): {lib().dgr_last_error().decode()}')
 
 
+_FN = {}
+
+
 def call(name, *args):
-  _check(getattr(lib(), name)(*args), name)
+  fn = _FN.get(name)
+  if fn is None:
+    fn = _FN[name] = getattr(lib(), name)
+  status = fn(*args)
+  if status != 0:
+    _check(status, name)
 
 
 _checked_devices = set()
@@ -116,8 +124,22 @@ def ptr(t):
   return 0 if t is None else t.data_ptr()
 
 
+_STREAM = None
+
+
 def stream():
-  return torch.cuda.current_stream().cuda_stream
+  """Handle of the CUDA stream work is enqueued on.  torch.cuda.current_stream() costs ~12 us per
+  call, so the handle is looked up once per public entry point (refresh_stream) and cached."""
+  global _STREAM
+  if _STREAM is None:
+    _STREAM = torch.cuda.current_stream().cuda_stream
+  return _STREAM
+
+
+def refresh_stream():
+  global _STREAM
+  _STREAM = torch.cuda.current_stream().cuda_stream
+  return _STREAM
 
 
 def _chk(t, dtype, name):
@@ -191,20 +213,31 @@ def keyspec_build(minmax, ncols, margin=32):
 
 
 def unique_first(coords, spec):
-  """-> (table, sel int32 [n] (first m valid), inverse int32 [n], n_unique device int32 [1])."""
+  """-> (table, sel int32 [n] (first m valid), inverse int32 [n], cnt device int32 [2] =
+  (n_unique, key-overflow flag))."""
   _chk(coords, torch.int32, 'coords')
   n, ncols = coords.shape
   dev = coords.device
   table = HashTable(n, dev)
   sel = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
   inverse = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-  cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+  cnt = torch.zeros(2, dtype=torch.int32, device=dev)
   slot = scratch('uf_slot', max(n, 1), torch.int32, dev)
   rank = scratch('uf_rank', max(n, 1), torch.int32, dev)
   scan = scratch('uf_scan', lib().dgr_scan_ws_elems(n), torch.int32, dev)
   call('dgr_unique_first', ptr(coords), n, ncols, ptr(spec), ptr(table.keys), ptr(table.vals), table.cap,
        ptr(sel), ptr(inverse), ptr(cnt), ptr(slot), ptr(rank), ptr(scan), stream())
   return table, sel, inverse, cnt
+
+
+def read_count(cnt):
+  """Host read of unique_first's (count, overflow) pair; raises on key overflow."""
+  global D2H_BYTES
+  n, overflow = cnt.cpu().tolist()
+  D2H_BYTES += 8
+  if overflow:
+    raise DgrError('coordinate extent does not fit a 63-bit packed key')
+  return n
 
 
 def hash_find(coords, spec, table):
@@ -258,11 +291,14 @@ def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
   call('dgr_kernel_map_table', ptr(out_coords), n_out, ncols, ptr(spec), ptr(in_table.keys),
        ptr(in_table.vals), in_table.cap, ptr(offsets), K, ptr(nbr), stream())
   ws = scratch('km_ws', lib().dgr_kmap_ws_elems(K, n_out), torch.int32, dev)
-  kofs = torch.empty(K + 1, dtype=torch.int32, device=dev)
-  call('dgr_kernel_map_count', ptr(nbr), K, n_out, ptr(ws), ptr(kofs), stream())
-  kofs_host = kofs.cpu().numpy()          # the one host read of this map: P and the tile count
+  kofs = torch.empty(K + 2, dtype=torch.int32, device=dev)
+  call('dgr_kernel_map_count', ptr(nbr), K, n_out, ptr(ws), ptr(kofs), ptr(spec), stream())
+  kofs_all = kofs.cpu().numpy()           # the one host read of this map: P, tile count, key check
   global D2H_BYTES
-  D2H_BYTES += kofs_host.nbytes
+  D2H_BYTES += kofs_all.nbytes
+  if kofs_all[K + 1] != 0:
+    raise DgrError('coordinate extent does not fit a 63-bit packed key')
+  kofs_host = kofs_all[:K + 1]
   P = int(kofs_host[K])
   counts = kofs_host[1:] - kofs_host[:-1]
   n_tiles = int(((counts + TILE_ROWS - 1) // TILE_ROWS).sum())

@@ -94,6 +94,7 @@ class DeepGlobalRegistration:
     """Stage 0: voxelise.  -> (xyz float32 [N,3], coords int32 [N,4], feats [N,1]).
     One GPU pass replaces sparse_quantize + the re-flooring of the reference (:134-161):
     floor(xyz / voxel) in the input dtype, first point per voxel, ascending indices."""
+    _abi.refresh_stream()
     if isinstance(pcd, np.ndarray):
       xyz = pcd
     elif isinstance(pcd, torch.Tensor):
@@ -111,8 +112,7 @@ class DeepGlobalRegistration:
     raw_coords, minmax = _abi.quantize_points(dxyz, self.voxel_size, batch=_batch)
     spec = _abi.keyspec_build(minmax, 4, KEY_MARGIN)
     table, sel, _, cnt = _abi.unique_first(raw_coords, spec)
-    npts = int(cnt.item())
-    CoordinateManager._check_spec(spec)
+    npts = _abi.read_count(cnt)
     sel = sel[:npts]
     coords = _abi.gather_rows_i32(raw_coords, sel, npts)
     xyz_sel = dxyz[sel.long()].float()
@@ -133,6 +133,7 @@ class DeepGlobalRegistration:
     forward passes - at half the launches and host synchronisations."""
     n0 = coords0.shape[0]
     coords = torch.cat((coords0, coords1), 0)
+    coords._dgr_manager = CoordinateManager(coords, assume_unique=True)   # two unique sets, batch 0 / 1
     feats = torch.ones(coords.shape[0], 1, device=self.device)
     F = self.fcgf_model.forward_fused(SparseTensor(feats, coordinates=coords, device=self.device)).F
     return F[:n0], F[n0:]
@@ -172,6 +173,7 @@ class DeepGlobalRegistration:
   def register(self, xyz0, xyz1, inlier_thr=0.00):
     """Main algorithm.  -> 4x4 float64 ndarray mapping cloud 0 into cloud 1's frame."""
     self.reg_timer.tic()
+    _abi.refresh_stream()
     with torch.no_grad():
       xyz0, coords0, feats0 = self.preprocess(xyz0, 0, _batch=0)
       xyz1, coords1, feats1 = self.preprocess(xyz1, 1, _batch=1)
@@ -189,9 +191,18 @@ class DeepGlobalRegistration:
         corres_idx0 = torch.arange(len(idx1), device=self.device)
         inlier_feats = self.inlier_feature_generation(xyz0, xyz1, coords0, coords1, fcgf_feats0,
                                                       fcgf_feats1, corres_idx0, idx1.long())
+      # rows are distinct by construction (idx0 = arange over unique voxels)
+      inlier_coords._dgr_manager = CoordinateManager(inlier_coords, assume_unique=True)
       logit = self.inlier_prediction(inlier_feats.contiguous(), coords=inlier_coords)
       weights, wsum_dev = _abi.sigmoid_clip_sum(logit, self.clip_weight_thresh)
-      wsum = float(wsum_dev.item())
+      # Procrustes + refinement are launched before the weight-sum gate is known (0.6 ms of GPU
+      # time in the rare safeguard case) so that gate and pose come back in ONE host read
+      res_dev = _abi.se3_register(xyz0, xyz1, weights.reshape(-1), idx1=idx1,
+                                  quantization_size=2 * self.voxel_size, max_iter=1000, max_break_count=20,
+                                  break_threshold_ratio=1e-4)
+      host = torch.cat((res_dev, wsum_dev.view(torch.float32))).cpu()
+      res = host[:16].numpy()
+      wsum = float(host[16:18].view(torch.float64)[0])
 
     wsum_threshold = max(200, len(weights) * 0.05)
     sign = '>=' if wsum >= wsum_threshold else '<'
@@ -200,9 +211,6 @@ class DeepGlobalRegistration:
     T = np.identity(4)
     self.last_info = dict(wsum=wsum, n0=len(weights), n1=len(xyz1))
     if wsum >= wsum_threshold:
-      res = _abi.se3_register(xyz0, xyz1, weights.reshape(-1), idx1=idx1,
-                              quantization_size=2 * self.voxel_size, max_iter=1000, max_break_count=20,
-                              break_threshold_ratio=1e-4).cpu().numpy()
       T[0:3, 0:3] = res[:9].reshape(3, 3)
       T[0:3, 3] = res[9:12]
       self.last_branch = 'procrustes'

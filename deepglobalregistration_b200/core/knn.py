@@ -11,6 +11,7 @@ def find_knn_gpu(F0, F1, nn_max_n=-1, knn=1, return_distance=False):
   if knn != 1:
     raise NotImplementedError('the DGR inference path uses knn=1 (core/deep_global_registration.py:178)')
   dev = _abi.require_device(F0.device)
+  _abi.refresh_stream()
   F0 = F0.to(dev, torch.float32).contiguous()
   F1 = F1.to(dev, torch.float32).contiguous()
   idx, dist = _abi.knn_top1(F0, F1, return_distance=True)

@@ -16,6 +16,7 @@ def _prep(X, Y, w):
     Y = torch.from_numpy(Y)
   dev = X.device if X.is_cuda else torch.device('cuda')
   dev = _abi.require_device(dev)
+  _abi.refresh_stream()
   X = X.to(dev, torch.float32).contiguous()
   Y = Y.to(dev, torch.float32).contiguous()
   if w is None:

@@ -226,7 +226,10 @@ __global__ void inverse_kernel(const int32_t* __restrict__ slot, const int32_t* 
   if (r < n) inverse[r] = vals[slot[r]];
 }
 
-__global__ void copy_total_kernel(const int32_t* src, int32_t* dst) { *dst = *src; }
+__global__ void copy_total_kernel(const int32_t* src, const dgr_keyspec_t* spec, int32_t* dst) {
+  dst[0] = *src;
+  dst[1] = spec->overflow;   // one host read returns the count and the key-overflow flag
+}
 
 __global__ void hash_find_kernel(const int32_t* __restrict__ coords, int64_t n, int ncols,
                                  const dgr_keyspec_t* __restrict__ spec_p,
@@ -298,9 +301,11 @@ __global__ void kernel_map_table_kernel(const int32_t* __restrict__ out_coords, 
   }
 }
 
-__global__ void kofs_kernel(const int32_t* __restrict__ block_ofs, int K, int bpk, int32_t* kofs) {
+__global__ void kofs_kernel(const int32_t* __restrict__ block_ofs, int K, int bpk, int32_t* kofs,
+                            const dgr_keyspec_t* __restrict__ spec) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k <= K) kofs[k] = block_ofs[(int64_t)k * bpk];
+  if (k == K + 1) kofs[k] = spec != nullptr ? spec->overflow : 0;   // rides along with the host read
 }
 
 __global__ void kernel_map_fill_kernel(const int32_t* __restrict__ nbr, int64_t n_out,
@@ -420,7 +425,7 @@ int32_t dgr_unique_first(const int32_t* coords, int64_t n, int32_t ncols, const 
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t mask = (uint64_t)cap - 1;
   if (n == 0) {
-    DGR_CUDA_CHECK(cudaMemsetAsync(n_unique, 0, sizeof(int32_t), st));
+    DGR_CUDA_CHECK(cudaMemsetAsync(n_unique, 0, 2 * sizeof(int32_t), st));
     return DGR_OK;
   }
   const unsigned nb = dgr_blocks(n, kScanElems);
@@ -431,7 +436,7 @@ int32_t dgr_unique_first(const int32_t* coords, int64_t n, int32_t ncols, const 
   scan_blocks_kernel<<<1, 1024, 0, st>>>(scan_ws, nb);
   unique_scatter_kernel<<<nb, kThreads, 0, st>>>(rank_ws, slot_ws, n, scan_ws, sel, vals);
   inverse_kernel<<<dgr_blocks(n, kThreads), kThreads, 0, st>>>(slot_ws, vals, n, inverse);
-  copy_total_kernel<<<1, 1, 0, st>>>(scan_ws + nb, n_unique);
+  copy_total_kernel<<<1, 1, 0, st>>>(scan_ws + nb, spec, n_unique);
   dgr_note_launches(7);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
@@ -492,13 +497,13 @@ int64_t dgr_kmap_ws_elems(int32_t K, int64_t n_out) {
 }
 
 int32_t dgr_kernel_map_count(const int32_t* nbr, int32_t K, int64_t n_out, int32_t* block_ws,
-                             int32_t* kofs, void* stream) {
+                             int32_t* kofs, const dgr_keyspec_t* spec, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned bpk = dgr_blocks(n_out, kScanElems);
   DGR_ARG_CHECK(K <= 65535, "K too large");
   block_count_kernel<true><<<dim3(bpk, K), kThreads, 0, st>>>(nbr, n_out, block_ws);
   scan_blocks_kernel<<<1, 1024, 0, st>>>(block_ws, (int64_t)K * bpk);
-  kofs_kernel<<<dgr_blocks(K + 1, kThreads), kThreads, 0, st>>>(block_ws, K, (int)bpk, kofs);
+  kofs_kernel<<<dgr_blocks(K + 2, kThreads), kThreads, 0, st>>>(block_ws, K, (int)bpk, kofs, spec);
   dgr_note_launches(3);
   DGR_LAUNCH_CHECK();
   return DGR_OK;

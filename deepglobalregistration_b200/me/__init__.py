@@ -101,6 +101,7 @@ class SparseTensor:
     manager = coordinate_manager if coordinate_manager is not None else coords_manager
     assert isinstance(features, torch.Tensor), 'features must be a torch.Tensor'
     if manager is None:
+      _abi.refresh_stream()
       assert coordinates is not None, 'coordinates or a coordinate manager + key must be given'
       if device is None:
         device = features.device if features.is_cuda else coordinates.device

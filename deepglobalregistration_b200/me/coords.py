@@ -43,20 +43,28 @@ def kernel_offsets(kernel_size, D, tensor_stride, device):
   return torch.from_numpy(offs.astype(np.int32)).to(device)
 
 
+_OFFSET_CACHE = {}
+
+
 class CoordinateManager:
   """Holds, per tensor stride, the coordinate matrix [N_s, D+1] and its hash table, plus a
   cache of kernel maps keyed by (in_stride, out_stride, kernel_size)."""
 
-  def __init__(self, coordinates=None, *, _parts=None):
+  def __init__(self, coordinates=None, *, _parts=None, assume_unique=False):
     if _parts is not None:
       coords, spec, table = _parts
+    elif assume_unique:
+      # rows known to be distinct (DGR: first-occurrence voxels, arange-indexed correspondences):
+      # no host round trip here; the key-overflow flag is checked with the first kernel-map read
+      coords = coordinates
+      spec = _abi.keyspec_build(_abi.coords_minmax(coords), coords.shape[1], KEY_MARGIN)
+      table, _, _, _ = _abi.unique_first(coords, spec)
     else:
       coords = coordinates
       assert coords.is_cuda and coords.dtype == torch.int32 and coords.dim() == 2
       spec = _abi.keyspec_build(_abi.coords_minmax(coords), coords.shape[1], KEY_MARGIN)
       table, _, _, cnt = _abi.unique_first(coords, spec)
-      n_unique = int(cnt.item())
-      self._check_spec(spec)
+      n_unique = _abi.read_count(cnt)
       if n_unique != coords.shape[0]:
         raise ValueError(f'{coords.shape[0] - n_unique} duplicate coordinates: the DGR hot path feeds '
                          'unique coordinates (sparse_quantize output) and relies on row order')
@@ -88,15 +96,15 @@ class CoordinateManager:
       fine = self._map(stride // 2)
       floored = _abi.stride_coords(fine.coords, stride)
       table, sel, _, cnt = _abi.unique_first(floored, self.spec)
-      n = int(cnt.item())
+      n = _abi.read_count(cnt)
       self._maps[stride] = _Map(_abi.gather_rows_i32(floored, sel, n), table, n)
     return self._maps[stride]
 
   def _offs(self, kernel_size, stride):
-    k = (kernel_size, stride)
-    if k not in self._offsets:
-      self._offsets[k] = kernel_offsets(kernel_size, self.D, stride, self.device)
-    return self._offsets[k]
+    k = (kernel_size, self.D, stride, self.device)
+    if k not in _OFFSET_CACHE:          # process-wide: the offsets depend on nothing else
+      _OFFSET_CACHE[k] = kernel_offsets(kernel_size, self.D, stride, self.device)
+    return _OFFSET_CACHE[k]
 
   # -- kernel maps ----------------------------------------------------------------------------
   def kernel_map(self, in_key, conv_stride, kernel_size):

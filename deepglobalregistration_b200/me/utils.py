@@ -29,9 +29,7 @@ def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, 
   coords, minmax = _abi.quantize_points(c.contiguous(), 1.0)
   spec = _abi.keyspec_build(minmax, 4, 32)
   _, sel, inverse, cnt = _abi.unique_first(coords, spec)
-  n = int(cnt.item())
-  if int(spec[1].item()) != 0:
-    raise _abi.DgrError('coordinate extent does not fit a 63-bit packed key')
+  n = _abi.read_count(cnt)
   index = sel[:n].long()
   uniq = coords[index][:, 1:].contiguous()
   conv = (lambda t: t.cpu().numpy()) if is_np else (lambda t: t)

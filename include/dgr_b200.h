@@ -82,7 +82,7 @@ int32_t dgr_hash_clear(uint64_t* keys, int32_t* vals, int64_t cap, void* stream)
  * coordinate, deterministically:
  *   sel[0..m)      ascending first-occurrence rows,
  *   inverse[n]     row -> index into sel of its representative,
- *   *n_unique      m (device int32),
+ *   n_unique[2]    (m, spec->overflow) device int32 - one host read for both,
  * and leaves the table mapping key -> index into sel.  slot_ws[n], rank_ws[n] and
  * scan_ws[dgr_scan_ws_elems(n)] are int32 workspaces. */
 int32_t dgr_unique_first(const int32_t* coords, int64_t n, int32_t ncols, const dgr_keyspec_t* spec,
@@ -113,13 +113,14 @@ int32_t dgr_kernel_map_table(const int32_t* out_coords, int64_t n_out, int32_t n
                              const dgr_keyspec_t* spec, const uint64_t* in_keys,
                              const int32_t* in_vals, int64_t in_cap, const int32_t* offsets,
                              int32_t K, int32_t* nbr, void* stream);
-/* Pair lists sorted by (kappa, j): two calls around one host read of kofs[K] (= P).
- *   count: kofs[K+1] exclusive offsets of every bucket (device int32), block_ws
+/* Pair lists sorted by (kappa, j): two calls around one host read of kofs (kofs[K] = P).
+ *   count: kofs[K+2] (device int32): exclusive offsets of every bucket, then the key-overflow
+ *          flag of `spec` (may be NULL) so the same host read validates the keys; block_ws
  *          workspace of dgr_kmap_ws_elems(K, n_out) int32;
  *   fill : in_idx[P], out_idx[P]. */
 int64_t dgr_kmap_ws_elems(int32_t K, int64_t n_out);
 int32_t dgr_kernel_map_count(const int32_t* nbr, int32_t K, int64_t n_out, int32_t* block_ws,
-                             int32_t* kofs, void* stream);
+                             int32_t* kofs, const dgr_keyspec_t* spec, void* stream);
 int32_t dgr_kernel_map_fill(const int32_t* nbr, int32_t K, int64_t n_out, const int32_t* block_ws,
                             int32_t* in_idx, int32_t* out_idx, void* stream);
 /* Work list of the gather-GEMM-scatter kernel: tile t covers pairs
