@@ -41,7 +41,8 @@ SIGNATURES = {
     'dgr_hash_find': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _p],
     'dgr_gather_rows_i32': [_p, _p, _i64, _i32, _p, _p],
     'dgr_stride_coords': [_p, _i64, _i32, _i32, _p, _p],
-    'dgr_kernel_map_table': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _i32, _p, _p],
+    'dgr_bloom_build': [_p, _i64, _p, _i64, _p],
+    'dgr_kernel_map_table': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i32, _p, _p],
     'dgr_kmap_ws_elems': [_i32, _i64],
     'dgr_kernel_map_count': [_p, _i32, _i64, _p, _p, _p, _p],
     'dgr_kernel_map_fill': [_p, _i32, _i64, _p, _p, _p, _p],
@@ -178,12 +179,22 @@ def scratch(name, numel, dtype, device):
 # thin typed wrappers (allocate outputs / workspaces with torch, call the ABI)
 # --------------------------------------------------------------------------- #
 class HashTable:
-  __slots__ = ('keys', 'vals', 'cap')
+  __slots__ = ('keys', 'vals', 'cap', '_bloom')
+
+  def bloom(self):
+    """(words, n_bits) miss filter, built on first use by a kernel map."""
+    if getattr(self, '_bloom', None) is None:
+      bits = 16 * self.cap
+      words = torch.empty(bits // 32, dtype=torch.int32, device=self.keys.device)
+      call('dgr_bloom_build', ptr(self.keys), self.cap, ptr(words), bits, stream())
+      self._bloom = (words, bits)
+    return self._bloom
 
   def __init__(self, n, device):
     self.cap = max(1024, next_pow2(2 * max(int(n), 1)))
     self.keys = torch.empty(self.cap, dtype=torch.int64, device=device)
     self.vals = torch.empty(self.cap, dtype=torch.int32, device=device)
+    self._bloom = None
     call('dgr_hash_clear', ptr(self.keys), ptr(self.vals), self.cap, stream())
 
 
@@ -288,8 +299,10 @@ def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
     nbr = torch.empty(K, max(n_out, 1), dtype=torch.int32, device=dev)
   else:
     nbr = scratch('km_nbr', K * max(n_out, 1), torch.int32, dev).view(K, max(n_out, 1))
+  # the miss filter pays off when most probes miss: many offsets per row (6-D, 5^3, 7^3 kernels)
+  bloom, bloom_bits = in_table.bloom() if K > 27 else (None, 0)
   call('dgr_kernel_map_table', ptr(out_coords), n_out, ncols, ptr(spec), ptr(in_table.keys),
-       ptr(in_table.vals), in_table.cap, ptr(offsets), K, ptr(nbr), stream())
+       ptr(in_table.vals), in_table.cap, ptr(bloom), bloom_bits, ptr(offsets), K, ptr(nbr), stream())
   ws = scratch('km_ws', lib().dgr_kmap_ws_elems(K, n_out), torch.int32, dev)
   kofs = torch.empty(K + 2, dtype=torch.int32, device=dev)
   call('dgr_kernel_map_count', ptr(nbr), K, n_out, ptr(ws), ptr(kofs), ptr(spec), stream())

@@ -261,11 +261,19 @@ knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1
         const int jc = j0 + cc * 32;
         if (jc < col_end) {
           if (jc + 32 <= col_end) {
+            // both passes reduce the chunk to its minimum first (branch-free); pass 2 walks the
+            // chunk element by element only when that minimum is within the candidate bound
+            float cmin = __int_as_float(0x7f800000);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const float g = hb[cc * 32 + q] - __uint_as_float(cur[q]);
-              if (PASS == 1) rmin = fminf(rmin, g);
-              else if (g <= th) knn_exact_candidate<C>(f0, f1, gi, jc + q, best_s, best_d2, best_j);
+            for (int q = 0; q < 32; ++q) cmin = fminf(cmin, hb[cc * 32 + q] - __uint_as_float(cur[q]));
+            if (PASS == 1) {
+              rmin = fminf(rmin, cmin);
+            } else if (cmin <= th) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                const float g = hb[cc * 32 + q] - __uint_as_float(cur[q]);
+                if (g <= th) knn_exact_candidate<C>(f0, f1, gi, jc + q, best_s, best_d2, best_j);
+              }
             }
           } else {
 #pragma unroll

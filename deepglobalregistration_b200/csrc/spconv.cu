@@ -263,19 +263,30 @@ spconv_table_kernel(const float* __restrict__ in_feat, int cin, const float* __r
       w_s[e] = weight[(int64_t)k0 * cin * COUT + e];
     __syncthreads();
     if (j < n_out) {
-      for (int kk = 0; kk < kn; ++kk) {
-        int i = nbr[(int64_t)(k0 + kk) * n_out + j];
-        if (i < 0) continue;
-        for (int ci = 0; ci < cin; ++ci) {
-          const float x = in_feat[(int64_t)i * cin + ci];
-          const float4* wr = reinterpret_cast<const float4*>(w_s + (kk * cin + ci) * COUT);
+      // the table reads are independent of everything else: keep 8 of them (and, for one input
+      // channel, the 8 gathered features) in flight instead of one dependent load per offset
+      for (int kb = 0; kb < kn; kb += 8) {
+        int idx[8];
+        float x0[8];
 #pragma unroll
-          for (int c4 = 0; c4 < COUT / 4; ++c4) {
-            float4 wv = wr[c4];
-            acc[4 * c4 + 0] = fmaf(x, wv.x, acc[4 * c4 + 0]);
-            acc[4 * c4 + 1] = fmaf(x, wv.y, acc[4 * c4 + 1]);
-            acc[4 * c4 + 2] = fmaf(x, wv.z, acc[4 * c4 + 2]);
-            acc[4 * c4 + 3] = fmaf(x, wv.w, acc[4 * c4 + 3]);
+        for (int u = 0; u < 8; ++u)
+          idx[u] = (kb + u < kn) ? __ldcs(nbr + (int64_t)(k0 + kb + u) * n_out + j) : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x0[u] = idx[u] >= 0 ? __ldg(in_feat + (int64_t)idx[u] * cin) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (idx[u] < 0) continue;
+          for (int ci = 0; ci < cin; ++ci) {
+            const float x = ci == 0 ? x0[u] : __ldg(in_feat + (int64_t)idx[u] * cin + ci);
+            const float4* wr = reinterpret_cast<const float4*>(w_s + ((kb + u) * cin + ci) * COUT);
+#pragma unroll
+            for (int c4 = 0; c4 < COUT / 4; ++c4) {
+              float4 wv = wr[c4];
+              acc[4 * c4 + 0] = fmaf(x, wv.x, acc[4 * c4 + 0]);
+              acc[4 * c4 + 1] = fmaf(x, wv.y, acc[4 * c4 + 1]);
+              acc[4 * c4 + 2] = fmaf(x, wv.z, acc[4 * c4 + 2]);
+              acc[4 * c4 + 3] = fmaf(x, wv.w, acc[4 * c4 + 3]);
+            }
           }
         }
       }
