@@ -18,6 +18,7 @@ copy of both scans and the D2H read of the pose.  `--impl reference` times the C
 port of the same path (MinkowskiEngine cannot be installed offline) on a bounded sample.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -41,6 +42,9 @@ SAMPLE_N_RAW = 8_000          # CPU sample: same generator, ~4k voxels per cloud
 SAMPLE_EXTENT = (1.5, 1.2, 1.0)
 VOXEL = 0.05
 POOL = 3                      # distinct pairs per rank, cycled over the steps
+
+
+_emit = print
 
 
 def log(*a):
@@ -181,7 +185,7 @@ def run_reference(args):
           'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
                            'sample': sample_desc(info)},
           'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-  print(json.dumps(line), flush=True)
+  _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------
@@ -258,6 +262,12 @@ def run_ours(args):
   n_warm = max(args.warmup, 3) * POOL
   timed(n_warm, host_inputs=False)
   timed(POOL, host_inputs=True)
+  # one untimed rehearsal of exactly the timed loops: flushes every lazy initialisation
+  # (allocator size classes, NCCL channels, pinned staging) out of the measurement
+  timed(args.steps, host_inputs=False)
+  timed(args.steps, host_inputs=True)
+  gc.collect()
+  gc.disable()
   log('[bench] warm-up done, timing')
 
   t_start = time.time()
@@ -326,7 +336,7 @@ def run_ours(args):
   h2d = int(sum(a.nbytes + b.nbytes for a, b, _ in pairs_host) / POOL)
   fixed_d2h = 2 * 8 + 8 + 9 * 4 + 8 + 64     # counts, spec flags, coarse-map sizes, wsum, pose
   line = {'metric': 'scan_pairs_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K,
-          'warmup': max(args.warmup, 3) * POOL + POOL, 'ms_per_step': res['ms'] / K, 'higher_is_better': True,
+          'warmup': max(args.warmup, 3) * POOL + POOL + 2 * K, 'ms_per_step': res['ms'] / K, 'higher_is_better': True,
           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
           'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d,
                   'd2h_bytes_per_step': int(res_e2e['d2h'] / K) + fixed_d2h,
@@ -340,12 +350,17 @@ def run_ours(args):
           'e2e_step_ms': {'min': min(res_e2e['steps_ms']), 'median': float(np.median(res_e2e['steps_ms'])),
                           'max': max(res_e2e['steps_ms'])},
           'published_reference': '0.69 s/pair without safeguard+ICP (reference assets/results.npz, unknown GPU)'}
-  print(json.dumps(line), flush=True)
+  _emit(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
 
 
 def main():
+  # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1
+  real_stdout = os.dup(1)
+  os.dup2(2, 1)
+  global _emit
+  _emit = lambda text: os.write(real_stdout, (text + '\n').encode())
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=20)
