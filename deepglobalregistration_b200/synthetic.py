@@ -141,31 +141,50 @@ def room_pair(seed, n_raw=250_000, extent=(3.6, 3.0, 2.5), rigid_copy=False, vox
   return xyz0, xyz1, T
 
 
-def lidar_scan(seed, pose_xy=(0.0, 0.0), n_beams=64, n_azimuth=1900, noise=0.02):
-  """KITTI-shape scan: 64 beams x 1900 azimuth steps over a ground plane and two
-  street walls; ~120k returns, ~18k voxels at 0.3 m."""
+def lidar_scan(seed, pose_xy=(0.0, 0.0), n_beams=64, n_azimuth=1900, noise=0.02, scan_id=0):
+  """KITTI-shape scan: 64 beams x 1900 azimuth steps over a ground plane, two street walls and
+  ~40 box obstacles (parked cars, poles) fixed in the WORLD frame, seen from a sensor at
+  pose_xy - so two poses along the street give genuinely different scans of one scene.
+  ~120k returns, ~16-18k voxels at 0.3 m.  Points are in the sensor frame."""
   rng = np.random.default_rng(20_000 + seed)
   wall_l, wall_r = rng.uniform(6, 14), -rng.uniform(6, 14)
   h = 1.73
+  n_obj = 40
+  cx = rng.uniform(-40, 60, n_obj)
+  cy = rng.uniform(wall_r + 1.0, wall_l - 1.0, n_obj)
+  sx, sy = rng.uniform(0.2, 2.2, n_obj), rng.uniform(0.2, 1.0, n_obj)
+  sz = rng.uniform(1.0, 3.0, n_obj)
+  lo = np.stack([cx - sx, cy - sy, np.full(n_obj, -h)], 1)
+  hi = np.stack([cx + sx, cy + sy, sz - h], 1)
+  keep_obj = (np.abs(cx - pose_xy[0]) > 3.0) | (np.abs(cy - pose_xy[1]) > 2.0)   # none on top of the sensor
+  lo, hi = lo[keep_obj], hi[keep_obj]
   elev = np.radians(np.linspace(-24.8, 2.0, n_beams))
   azim = np.linspace(-math.pi, math.pi, n_azimuth, endpoint=False)
   e, a = np.meshgrid(elev, azim, indexing='ij')
   d = np.stack([np.cos(e) * np.cos(a), np.cos(e) * np.sin(a), np.sin(e)], -1).reshape(-1, 3)
-  y0 = pose_xy[1]
+  x0, y0 = pose_xy
   with np.errstate(divide='ignore', invalid='ignore'):
     tg = np.where(d[:, 2] < 0, -h / d[:, 2], np.inf)
     tl = np.where(d[:, 1] > 0, (wall_l - y0) / d[:, 1], np.inf)
     tr = np.where(d[:, 1] < 0, (wall_r - y0) / d[:, 1], np.inf)
-  t = np.minimum(np.minimum(tg, tl), tr)
+    t = np.minimum(np.minimum(tg, tl), tr)
+    org = np.array([x0, y0, 0.0])
+    inv = 1.0 / d
+    for blo, bhi in zip(lo, hi):                      # slab test against every box
+      t1, t2 = (blo - org) * inv, (bhi - org) * inv
+      tn = np.nanmax(np.minimum(t1, t2), axis=1)
+      tf = np.nanmin(np.maximum(t1, t2), axis=1)
+      hit = (tn <= tf) & (tf > 0) & (tn > 0)
+      t = np.where(hit, np.minimum(t, tn), t)
   keep = t < 80.0
   p = d[keep] * t[keep, None]
-  p += np.random.default_rng(seed).normal(scale=noise, size=p.shape)
+  p += np.random.default_rng(1000 * seed + scan_id).normal(scale=noise, size=p.shape)
   return p
 
 
 def lidar_pair(seed, advance=10.0):
-  xyz0 = lidar_scan(seed, (0.0, 0.0))
-  xyz1 = lidar_scan(seed, (advance, 0.0))
+  xyz0 = lidar_scan(seed, (0.0, 0.0), scan_id=0)
+  xyz1 = lidar_scan(seed, (advance, 0.0), scan_id=1)
   T = np.eye(4)
   T[0, 3] = -advance  # a point at x in frame 0 sits at x-advance in frame 1
   return xyz0, xyz1, T
