@@ -138,3 +138,53 @@ def test_register_float32_and_lidar_shape(dgr, state):
   if taps['branch'] == 'procrustes':
     te, re = syn.rte_rre(T, T_o)
     assert te <= 1e-3 and re <= 1e-3, (te, re)
+
+
+def test_checkpoint_file_boundary(tmp_path, state):
+  """A checkpoint written with torch.save in the reference's layout (state_dict,
+  state_dict_inlier, pickled attribute-dict config; core/trainer.py:527-549) loads through
+  config.weights = <path> exactly like the in-memory dict."""
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+  path = tmp_path / 'ckpt.pth'
+  torch.save(state, path)
+  cfg = types.SimpleNamespace(weights=str(path), clip_weight_thresh=0.05, verbose=False)
+  d = DeepGlobalRegistration(cfg)
+  assert d.voxel_size == state['config']['voxel_size'] and cfg.inlier_feature_type == 'ones'
+  for k, v in state['state_dict'].items():
+    assert torch.equal(d.fcgf_model.state_dict()[k].cpu(), v), k
+  xyz0, xyz1, _ = syn.room_pair(5, n_raw=6000, extent=(1.2, 1.0, 0.8))
+  T = d.register(xyz0, xyz1)
+  assert T.shape == (4, 4) and np.isfinite(T).all()
+
+
+@pytest.mark.parametrize('n_raw', [1, 3, 40, 300])
+def test_register_tiny_clouds(dgr, state, n_raw):
+  """Degenerate sizes: single voxels, fewer voxels than one 128-row tile, empty coarse
+  neighbourhoods.  The weight-sum gate (>= 200) sends these to the safeguard branch, which
+  must be reported, not crash; every stage before it must still agree with the oracle."""
+  g = np.random.default_rng(n_raw)
+  xyz0 = g.uniform(0, 0.6, size=(n_raw, 3))
+  xyz1 = xyz0 + 0.05
+  T = dgr.register(xyz0, xyz1)
+  T_o, taps = op.register(state, xyz0, xyz1)
+  assert dgr.last_branch == taps['branch'] == 'safeguard'
+  assert np.array_equal(T, np.eye(4))
+  assert dgr.last_info['n0'] == len(taps['coords0'])
+  assert abs(dgr.last_info['wsum'] - taps['wsum']) <= 1e-3 * max(1.0, taps['wsum'])
+
+
+def test_preprocess_rejects_unknown_input(dgr):
+  with pytest.raises(Exception, match='Unrecognized pcd type'):
+    dgr.preprocess('not a point cloud')
+
+
+def test_unbuilt_stages_fail_loudly(dgr):
+  xyz0, xyz1, _ = syn.room_pair(6, n_raw=4000, extent=(1.0, 1.0, 0.8))
+  dgr.use_icp = True
+  try:
+    with pytest.raises(NotImplementedError):
+      dgr.register(xyz0, xyz1)
+  finally:
+    dgr.use_icp = False
+  with pytest.raises(NotImplementedError):
+    dgr.safeguard_registration()
