@@ -65,45 +65,83 @@ def base_config(n_gpus):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+  """SM clock and throttle reasons during the timed region.  Uses NVML in-process (a query costs
+  microseconds); spawning nvidia-smi in a loop was measured to stall the CUDA driver for ~200 ms
+  per query on these hosts and is only the fallback."""
   Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
        'clocks_event_reasons.sw_power_cap')
 
-  def __init__(self, index):
-    self.rows, self.proc = [], None
+  def __init__(self, index, period=0.1):
+    self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+    self.period = period
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nvml = pynvml
+      # torch's device index follows CUDA_VISIBLE_DEVICES; map through the UUID-free common case
+      vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+      phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+      self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+      self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+      self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+      self.thread.start()
+      return
+    except Exception as e:   # noqa: BLE001
+      log('NVML sampler unavailable (%s); falling back to nvidia-smi' % e)
+      self.nvml = None
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
-                                    '--format=csv,noheader,nounits', '-lms', '200'],
+                                    '--format=csv,noheader,nounits', '-lms', '500'],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
     except Exception as e:   # noqa: BLE001
       log('clock sampler unavailable:', e)
 
-  def _read(self):
-    for line in self.proc.stdout:
-      self.rows.append((time.time(), line.strip()))
+  def _poll_nvml(self):
+    n = self.nvml
+    names = {'hw_slowdown': getattr(n, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+             'hw_thermal_slowdown': getattr(n, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+             'sw_thermal_slowdown': getattr(n, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+             'sw_power_cap': getattr(n, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+    get_reasons = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons',
+                          getattr(n, 'nvmlDeviceGetCurrentClocksThrottleReasons', None))
+    while not self.stop_flag:
+      try:
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        mask = int(get_reasons(self.handle)) if get_reasons else 0
+        active = [k for k, bit in names.items() if mask & bit]
+        self.rows.append((time.time(), sm, active))
+      except Exception:   # noqa: BLE001
+        pass
+      time.sleep(self.period)
 
-  def stop(self, t0, t1):
-    if self.proc is None:
-      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-    self.proc.terminate()
-    sm, mx, reasons = [], None, set()
+  def _read(self):
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for ts, line in self.rows:
-      if not (t0 - 0.05 <= ts <= t1 + 0.15):
-        continue
+    for line in self.proc.stdout:
       f = [x.strip() for x in line.split(',')]
       try:
-        sm.append(float(f[0]))
-        mx = float(f[1])
-        for nm, v in zip(names, f[3:7]):
-          if v.lower().startswith('active'):
-            reasons.add(nm)
+        self.max_sm = float(f[1])
+        self.rows.append((time.time(), float(f[0]),
+                          [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith('active')]))
       except (ValueError, IndexError):
         continue
-    return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'samples': len(sm),
-            'reasons': sorted(reasons)}
+
+  def stop(self, t0, t1):
+    self.stop_flag = True
+    if self.proc is not None:
+      self.proc.terminate()
+    if self.proc is None and self.nvml is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+    sm, reasons = [], set()
+    for ts, clk, active in self.rows:
+      if t0 - 0.05 <= ts <= t1 + 0.15:
+        sm.append(clk)
+        reasons.update(active)
+    return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': getattr(self, 'max_sm', None),
+            'samples': len(sm), 'reasons': sorted(reasons),
+            'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # ------------------------------------------------------------------------------------------

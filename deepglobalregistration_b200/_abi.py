@@ -42,9 +42,9 @@ SIGNATURES = {
     'dgr_gather_rows_i32': [_p, _p, _i64, _i32, _p, _p],
     'dgr_stride_coords': [_p, _i64, _i32, _i32, _p, _p],
     'dgr_bloom_build': [_p, _i64, _p, _i64, _p],
-    'dgr_kernel_map_table': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i32, _p, _p],
+    'dgr_kernel_map_table': [_p, _i64, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p],
     'dgr_kmap_ws_elems': [_i32, _i64],
-    'dgr_kernel_map_count': [_p, _i32, _i64, _p, _p, _p, _p],
+    'dgr_kernel_map_count': [_p, _i32, _i64, _p, _i32, _p, _p, _p],
     'dgr_kernel_map_fill': [_p, _i32, _i64, _p, _p, _p, _p],
     'dgr_kernel_map_tiles': [_p, _i32, _i32, _i32, _p, _p, _p],
     'dgr_spconv_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
@@ -301,11 +301,11 @@ def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
     nbr = scratch('km_nbr', K * max(n_out, 1), torch.int32, dev).view(K, max(n_out, 1))
   # the miss filter pays off when most probes miss: many offsets per row (6-D, 5^3, 7^3 kernels)
   bloom, bloom_bits = in_table.bloom() if K > 27 else (None, 0)
-  call('dgr_kernel_map_table', ptr(out_coords), n_out, ncols, ptr(spec), ptr(in_table.keys),
-       ptr(in_table.vals), in_table.cap, ptr(bloom), bloom_bits, ptr(offsets), K, ptr(nbr), stream())
   ws = scratch('km_ws', lib().dgr_kmap_ws_elems(K, n_out), torch.int32, dev)
+  call('dgr_kernel_map_table', ptr(out_coords), n_out, ncols, ptr(spec), ptr(in_table.keys),
+       ptr(in_table.vals), in_table.cap, ptr(bloom), bloom_bits, ptr(offsets), K, ptr(nbr), ptr(ws), stream())
   kofs = torch.empty(K + 2, dtype=torch.int32, device=dev)
-  call('dgr_kernel_map_count', ptr(nbr), K, n_out, ptr(ws), ptr(kofs), ptr(spec), stream())
+  call('dgr_kernel_map_count', ptr(nbr), K, n_out, ptr(ws), 1, ptr(kofs), ptr(spec), stream())
   kofs_all = kofs.cpu().numpy()           # the one host read of this map: P, tile count, key check
   global D2H_BYTES
   D2H_BYTES += kofs_all.nbytes

@@ -164,7 +164,8 @@ __global__ void block_count_kernel(const int32_t* __restrict__ v, int64_t n, int
 }
 
 // single-block exclusive scan in place over nb entries; entry nb receives the total.
-__global__ void scan_blocks_kernel(int32_t* cnt, int64_t nb) {
+__global__ void scan_blocks_kernel(int32_t* cnt, int64_t nb, int32_t* kofs = nullptr, int K = 0, int bpk = 0,
+                                   const dgr_keyspec_t* spec = nullptr) {
   __shared__ int carry_s;
   __shared__ int wsum[32];
   if (threadIdx.x == 0) carry_s = 0;
@@ -194,6 +195,11 @@ __global__ void scan_blocks_kernel(int32_t* cnt, int64_t nb) {
     __syncthreads();
   }
   if (threadIdx.x == 0) cnt[nb] = carry_s;
+  if (kofs != nullptr) {   // bucket offsets of a kernel map (+ the key-overflow flag), same launch
+    __syncthreads();
+    for (int k = threadIdx.x; k <= K + 1; k += blockDim.x)
+      kofs[k] = (k <= K) ? cnt[(int64_t)k * bpk] : (spec != nullptr ? spec->overflow : 0);
+  }
 }
 
 // rank winners: sel[rank] = row, table value <- rank
@@ -298,7 +304,7 @@ __global__ void kernel_map_table_kernel(const int32_t* __restrict__ out_coords, 
                                         const int32_t* __restrict__ vals, uint64_t mask,
                                         const uint32_t* __restrict__ bloom, uint64_t bit_mask,
                                         const int32_t* __restrict__ offsets, int K,
-                                        int32_t* __restrict__ nbr) {
+                                        int32_t* __restrict__ nbr, int32_t* block_cnt, int bpk) {
   __shared__ long long delta[kKappaChunk];
   const dgr_keyspec_t s = *spec_p;
   const int k0 = blockIdx.y * kKappaChunk;
@@ -311,13 +317,15 @@ __global__ void kernel_map_table_kernel(const int32_t* __restrict__ out_coords, 
   }
   __syncthreads();
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_out) return;
-  const uint64_t key = dgr_pack_key(out_coords + j * ncols, s);
+  const bool live = j < n_out;
+  const uint64_t key = live ? dgr_pack_key(out_coords + j * ncols, s) : 0;
   int32_t* dst = nbr + (int64_t)k0 * n_out + j;
+  const int cnt_col = (int)(((int64_t)blockIdx.x * blockDim.x) / kScanElems);   // 2048-row counting block
   for (int kk = 0; kk < kn; kk += 4) {
     // four independent probes in flight: filter words first, table only on a filter hit
     uint64_t q[4];
     bool maybe[4];
+    int32_t found[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       q[u] = key + (uint64_t)delta[min(kk + u, kn - 1)];
@@ -329,8 +337,18 @@ __global__ void kernel_map_table_kernel(const int32_t* __restrict__ out_coords, 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (kk + u < kn) dst[(int64_t)(kk + u) * n_out] = maybe[u] ? dgr_hash_lookup(keys, vals, mask, q[u]) : -1;
+    for (int u = 0; u < 4; ++u) {
+      found[u] = (live && kk + u < kn && maybe[u]) ? dgr_hash_lookup(keys, vals, mask, q[u]) : -1;
+      if (live && kk + u < kn) dst[(int64_t)(kk + u) * n_out] = found[u];
+    }
+    if (block_cnt != nullptr) {     // fused population count: saves a full pass over the table
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = __syncthreads_count(found[u] >= 0);
+        if (threadIdx.x == 0 && kk + u < kn && c > 0)
+          atomicAdd(block_cnt + (int64_t)(k0 + kk + u) * bpk + cnt_col, c);
+      }
+    }
   }
 }
 
@@ -367,24 +385,43 @@ __global__ void kernel_map_fill_kernel(const int32_t* __restrict__ nbr, int64_t 
 
 __global__ void tiles_kernel(const int32_t* __restrict__ kofs, int K, int tile_rows, int n_tiles,
                              int32_t* __restrict__ tile_k, int32_t* __restrict__ tile_start) {
-  extern __shared__ int tofs[];   // K + 1
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int k = 0; k < K; ++k) {
-      tofs[k] = acc;
-      acc += (kofs[k + 1] - kofs[k] + tile_rows - 1) / tile_rows;
+  extern __shared__ int tofs[];   // K + 1 exclusive tile offsets
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < K; base += blockDim.x) {   // block-wide scan, 1024 buckets per round
+    const int k = base + threadIdx.x;
+    const int v = k < K ? (kofs[k + 1] - kofs[k] + tile_rows - 1) / tile_rows : 0;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
     }
-    tofs[K] = acc;
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      const int sm = wsum[w];
+      if (w < warp) wbase += sm;
+      tot += sm;
+    }
+    const int carry = carry_s;
+    if (k < K) tofs[k] = carry + wbase + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
   }
+  if (threadIdx.x == 0) tofs[K] = carry_s;
   __syncthreads();
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
-    int lo = 0, hi = K;   // largest k with tofs[k] <= t
+    int lo = 0, hi = K;   // largest k with tofs[k] <= t (non-empty: tofs[k + 1] > t)
     while (hi - lo > 1) {
       int mid = (lo + hi) >> 1;
       if (tofs[mid] <= t) lo = mid; else hi = mid;
     }
-    // skip empty buckets that share the same tofs value
-    while (lo + 1 < K && tofs[lo + 1] <= t) ++lo;
     tile_k[t] = lo;
     tile_start[t] = kofs[lo] + (t - tofs[lo]) * tile_rows;
   }
@@ -396,6 +433,8 @@ __global__ void tiles_kernel(const int32_t* __restrict__ kofs, int K, int tile_r
 // C ABI
 // =========================================================================================
 extern "C" {
+
+int64_t dgr_kmap_ws_elems(int32_t K, int64_t n_out);
 
 int32_t dgr_coords_minmax(const int32_t* coords, int64_t n, int32_t ncols, int32_t* minmax,
                           void* stream) {
@@ -523,16 +562,20 @@ int32_t dgr_kernel_map_table(const int32_t* out_coords, int64_t n_out, int32_t n
                              const dgr_keyspec_t* spec, const uint64_t* in_keys,
                              const int32_t* in_vals, int64_t in_cap, const uint32_t* bloom,
                              int64_t bloom_bits, const int32_t* offsets, int32_t K, int32_t* nbr,
-                             void* stream) {
+                             int32_t* block_cnt, void* stream) {
   DGR_ARG_CHECK(bloom == nullptr || (bloom_bits >= 32 && (bloom_bits & (bloom_bits - 1)) == 0),
                 "bloom_bits must be a power of two");
   DGR_ARG_CHECK(in_cap > 0 && (in_cap & (in_cap - 1)) == 0, "capacity must be a power of two");
   DGR_ARG_CHECK(K >= 1, "K must be positive");
+  if (block_cnt != nullptr)
+    DGR_CUDA_CHECK(cudaMemsetAsync(block_cnt, 0, (size_t)dgr_kmap_ws_elems(K, n_out) * sizeof(int32_t),
+                                   (cudaStream_t)stream));
   if (n_out == 0) return DGR_OK;
   dim3 grid(dgr_blocks(n_out, kThreads), (K + kKappaChunk - 1) / kKappaChunk);
   kernel_map_table_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
       out_coords, n_out, ncols, spec, in_keys, in_vals, (uint64_t)in_cap - 1, bloom,
-      bloom != nullptr ? (uint64_t)bloom_bits - 1 : 0, offsets, K, nbr);
+      bloom != nullptr ? (uint64_t)bloom_bits - 1 : 0, offsets, K, nbr, block_cnt,
+      (int)dgr_blocks(n_out, kScanElems));
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
@@ -545,14 +588,13 @@ int64_t dgr_kmap_ws_elems(int32_t K, int64_t n_out) {
 }
 
 int32_t dgr_kernel_map_count(const int32_t* nbr, int32_t K, int64_t n_out, int32_t* block_ws,
-                             int32_t* kofs, const dgr_keyspec_t* spec, void* stream) {
+                             int32_t counts_ready, int32_t* kofs, const dgr_keyspec_t* spec, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned bpk = dgr_blocks(n_out, kScanElems);
   DGR_ARG_CHECK(K <= 65535, "K too large");
-  block_count_kernel<true><<<dim3(bpk, K), kThreads, 0, st>>>(nbr, n_out, block_ws);
-  scan_blocks_kernel<<<1, 1024, 0, st>>>(block_ws, (int64_t)K * bpk);
-  kofs_kernel<<<dgr_blocks(K + 2, kThreads), kThreads, 0, st>>>(block_ws, K, (int)bpk, kofs, spec);
-  dgr_note_launches(3);
+  if (!counts_ready) block_count_kernel<true><<<dim3(bpk, K), kThreads, 0, st>>>(nbr, n_out, block_ws);
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(block_ws, (int64_t)K * bpk, kofs, K, (int)bpk, spec);
+  dgr_note_launches(counts_ready ? 1 : 2);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
 }

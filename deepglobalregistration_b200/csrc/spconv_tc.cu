@@ -49,6 +49,9 @@ __device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, un
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -61,7 +64,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 }
 
 struct TcShared {
-  unsigned long long full[4];
+  unsigned long long full[4];      // gathered A tiles (256 arrivals) + B hi tile (bulk-copy bytes)
+  unsigned long long full_lo[4];   // B lo tile (bulk-copy bytes): needed only by the third product
   unsigned long long empty[4];
   unsigned long long acc_full[2];
   unsigned long long acc_empty[2];
@@ -93,6 +97,7 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
   if (t == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(smem_u32(&sh.full[s]), kLoaderThreads);
+      mbar_init(smem_u32(&sh.full_lo[s]), 1);
       mbar_init(smem_u32(&sh.empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -159,9 +164,14 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
         unsigned char* a_hi = stage0 + (size_t)s * stage_bytes;
         unsigned char* a_lo = a_hi + kATileBytes;
         if (t == 0) {
-          mbar_expect_tx(smem_u32(&sh.full[s]), slab_bytes);
-          bulk_g2s(smem_u32(a_lo + kATileBytes), slab + (size_t)c * (slab_bytes / 4), slab_bytes,
-                   smem_u32(&sh.full[s]));
+          // hi tile first, on the barrier the first two products wait for; the lo tile lands on its
+          // own barrier while those products already run
+          const float* src = slab + (size_t)c * (slab_bytes / 4);
+          mbar_expect_tx(smem_u32(&sh.full[s]), (uint32_t)b_tile_bytes);
+          bulk_g2s(smem_u32(a_lo + kATileBytes), src, (uint32_t)b_tile_bytes, smem_u32(&sh.full[s]));
+          mbar_arrive_expect_tx(smem_u32(&sh.full_lo[s]), (uint32_t)b_tile_bytes);
+          bulk_g2s(smem_u32(a_lo + kATileBytes + b_tile_bytes), src + b_tile_bytes / 4, (uint32_t)b_tile_bytes,
+                   smem_u32(&sh.full_lo[s]));
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) split_store(a_cur[i], a_hi, a_lo, a_off + i * 4096);
@@ -193,17 +203,23 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
           const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_bytes);
           const uint32_t a_lo = a_hi + kATileBytes;
           const uint32_t b_hi = a_lo + kATileBytes;
-          const uint32_t b_lo = b_hi + b_tile_bytes;
 #pragma unroll
-          for (int ks = 0; ks < kChunk / 8; ++ks) {
+          for (int ks = 0; ks < kChunk / 8; ++ks) {   // hi*hi and lo*hi need only the B hi tile
             const uint32_t ko = ks * 32;   // 8 tf32 = 32 bytes along K inside the swizzle row
-            const uint64_t dah = umma_desc(a_hi + ko), dal = umma_desc(a_lo + ko);
-            const uint64_t dbh = umma_desc(b_hi + ko), dbl = umma_desc(b_lo + ko);
-            tc_mma_tf32(tmem_d, dah, dbh, idesc, (c | ks) != 0);
-            if (passes == 3) {
-              tc_mma_tf32(tmem_d, dal, dbh, idesc, 1);
-              tc_mma_tf32(tmem_d, dah, dbl, idesc, 1);
-            }
+            const uint64_t dbh = umma_desc(b_hi + ko);
+            tc_mma_tf32(tmem_d, umma_desc(a_hi + ko), dbh, idesc, (c | ks) != 0);
+            if (passes == 3) tc_mma_tf32(tmem_d, umma_desc(a_lo + ko), dbh, idesc, 1);
+          }
+        }
+        mbar_wait(smem_u32(&sh.full_lo[s]), ph);       // the B lo tile has landed meanwhile
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_bytes);
+          const uint32_t b_lo = a_hi + 2 * kATileBytes + b_tile_bytes;
+          if (passes == 3) {
+#pragma unroll
+            for (int ks = 0; ks < kChunk / 8; ++ks)
+              tc_mma_tf32(tmem_d, umma_desc(a_hi + ks * 32), umma_desc(b_lo + ks * 32), idesc, 1);
           }
           tc_commit(smem_u32(&sh.empty[s]));
           if (c == n_chunks - 1) tc_commit(smem_u32(&sh.acc_full[buf]));

@@ -108,7 +108,9 @@ int32_t dgr_stride_coords(const int32_t* coords, int64_t n, int32_t ncols, int32
  *      (model/residual_block.py:31-44,56-80) ----------------------------------------- */
 /* nbr[kappa * n_out + j] = row i of the input map with C_in[i] == C_out[j] + offsets[kappa]
  * or -1.  offsets is a DEVICE int32 [K, ncols-1] matrix (already scaled by the input
- * tensor stride), kappa enumerates axis 0 fastest. */
+ * tensor stride), kappa enumerates axis 0 fastest.  block_cnt (optional, dgr_kmap_ws_elems
+ * int32, zeroed by the call) receives the per-(kappa, 2048-row block) hit counts so that
+ * dgr_kernel_map_count(counts_ready = 1) need not read the table again. */
 /* Optional miss filter of a table: bloom[bloom_bits / 32] words, one hashed bit per stored key
  * (bloom_bits a power of two, 16 x capacity recommended).  With it, dgr_kernel_map_table
  * answers most misses (99.7 % of the probes of a 6-D map) from L1. */
@@ -117,7 +119,7 @@ int32_t dgr_kernel_map_table(const int32_t* out_coords, int64_t n_out, int32_t n
                              const dgr_keyspec_t* spec, const uint64_t* in_keys,
                              const int32_t* in_vals, int64_t in_cap, const uint32_t* bloom,
                              int64_t bloom_bits, const int32_t* offsets, int32_t K, int32_t* nbr,
-                             void* stream);
+                             int32_t* block_cnt, void* stream);
 /* Pair lists sorted by (kappa, j): two calls around one host read of kofs (kofs[K] = P).
  *   count: kofs[K+2] (device int32): exclusive offsets of every bucket, then the key-overflow
  *          flag of `spec` (may be NULL) so the same host read validates the keys; block_ws
@@ -125,7 +127,7 @@ int32_t dgr_kernel_map_table(const int32_t* out_coords, int64_t n_out, int32_t n
  *   fill : in_idx[P], out_idx[P]. */
 int64_t dgr_kmap_ws_elems(int32_t K, int64_t n_out);
 int32_t dgr_kernel_map_count(const int32_t* nbr, int32_t K, int64_t n_out, int32_t* block_ws,
-                             int32_t* kofs, const dgr_keyspec_t* spec, void* stream);
+                             int32_t counts_ready, int32_t* kofs, const dgr_keyspec_t* spec, void* stream);
 int32_t dgr_kernel_map_fill(const int32_t* nbr, int32_t K, int64_t n_out, const int32_t* block_ws,
                             int32_t* in_idx, int32_t* out_idx, void* stream);
 /* Work list of the gather-GEMM-scatter kernel: tile t covers pairs
