@@ -62,6 +62,7 @@ SIGNATURES = {
     'dgr_knn_top1_tc': [_p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p],
     'dgr_inlier_coords': [_p, _p, _p, _i64, _p, _p],
     'dgr_sigmoid_clip_sum': [_p, _i64, _f32, _p, _p, _p],
+    'dgr_icp_point_to_point': [_p, _i64, _p, _p, _p, _p, _i64, _i32, _f64, _f64, _p, _i32, _f64, _f64, _p, _p, _p],
     'dgr_se3_register': [_p, _p, _p, _p, _i64, _f32, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p],
 }
 _RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_knn_tc_ws_elems': _i64, 'dgr_launch_count': _i64, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
@@ -474,4 +475,22 @@ def se3_register(x, y, w, idx1=None, quantization_size=1.0, max_iter=1000, max_b
   call('dgr_se3_register', ptr(x), ptr(y), ptr(idx1), ptr(w), n, float(quantization_size), int(max_iter),
        int(max_break_count), float(break_threshold_ratio), float(lr), float(gamma), ptr(pack), ptr(cnt),
        ptr(res), stream())
+  return res
+
+
+def icp_point_to_point(src, tgt, tgt_manager, voxel, max_dist, T_init, max_iter=30, rel_fitness=1e-6,
+                       rel_rmse=1e-6, batch=0):
+  """Point-to-point ICP (open3d defaults) of src onto tgt through tgt's voxel hash.
+  src / tgt: CUDA float32 [n, 3]; tgt_manager: the CoordinateManager preprocess() built for tgt;
+  T_init: 4x4 (numpy / tensor) or device double [12].  -> device double [20]."""
+  _chk(src, torch.float32, 'src'); _chk(tgt, torch.float32, 'tgt')
+  dev = src.device
+  m = tgt_manager._maps[1]
+  if not (isinstance(T_init, torch.Tensor) and T_init.is_cuda and T_init.numel() == 12):
+    T_init = torch.as_tensor(T_init, dtype=torch.float64).reshape(4, 4)[:3].contiguous().to(dev)
+  state = torch.empty(64, dtype=torch.float64, device=dev)
+  res = torch.empty(20, dtype=torch.float64, device=dev)
+  call('dgr_icp_point_to_point', ptr(src), src.shape[0], ptr(tgt), ptr(tgt_manager.spec), ptr(m.table.keys),
+       ptr(m.table.vals), m.table.cap, int(batch), float(voxel), float(max_dist), ptr(T_init), int(max_iter),
+       float(rel_fitness), float(rel_rmse), ptr(state), ptr(res), stream())
   return res

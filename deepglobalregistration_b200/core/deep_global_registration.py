@@ -2,9 +2,9 @@
 (core/deep_global_registration.py:68-324), every stage on libdgr_b200.
 
 Built path: voxelise -> FCGF features -> feature kNN -> 6-D inlier network -> weights ->
-weighted Procrustes + SE(3) refinement.  The open3d stages around it (RANSAC safeguard
-:302-315 and ICP :317-322) are SURVEY.md §8f "next" rows and are not built: ``use_icp``
-defaults to False and the safeguard branch returns identity with ``last_branch`` set.
+weighted Procrustes + SE(3) refinement -> point-to-point ICP (``use_icp``, default True as
+in the reference).  The open3d RANSAC safeguard (:302-315) is a SURVEY.md §8f "next" row and
+is not built: that branch returns identity with ``last_branch`` set to 'safeguard'.
 """
 import os
 
@@ -24,7 +24,7 @@ class DeepGlobalRegistration:
     self.clip_weight_thresh = self.config.clip_weight_thresh
     self.device = _abi.require_device(device)
     self.safeguard_method = 'correspondence'
-    self.use_icp = False          # reference default True; ICP is a "next" row
+    self.use_icp = True           # as the reference; GPU point-to-point ICP (dgr_icp_point_to_point)
     self.verbose = getattr(config, 'verbose', True)
     self.feat_timer = Timer()
     self.reg_timer = Timer()
@@ -200,9 +200,15 @@ class DeepGlobalRegistration:
       res_dev = _abi.se3_register(xyz0, xyz1, weights.reshape(-1), idx1=idx1,
                                   quantization_size=2 * self.voxel_size, max_iter=1000, max_break_count=20,
                                   break_threshold_ratio=1e-4)
-      host = torch.cat((res_dev, wsum_dev.view(torch.float32))).cpu()
-      res = host[:16].numpy()
-      wsum = float(host[16:18].view(torch.float64)[0])
+      parts = [res_dev.double(), wsum_dev]
+      if self.use_icp:
+        # ICP fine-tune (reference :317-322: open3d point-to-point ICP, radius 2 * voxel, initialised
+        # with the refined pose), through cloud 1's voxel hash; enqueued before the single readback
+        T12 = torch.cat((res_dev[:9].reshape(3, 3), res_dev[9:12].reshape(3, 1)), 1).double().contiguous()
+        parts.append(_abi.icp_point_to_point(xyz0, xyz1, coords1._dgr_manager, self.voxel_size,
+                                             2 * self.voxel_size, T12, batch=1))
+      host = torch.cat(parts).cpu().numpy()
+      res, wsum = host[:16], float(host[16])
 
     wsum_threshold = max(200, len(weights) * 0.05)
     sign = '>=' if wsum >= wsum_threshold else '<'
@@ -223,7 +229,9 @@ class DeepGlobalRegistration:
       self.reg_timer.toc()
       self._log('=> weight sum below threshold: the reference falls back to open3d RANSAC here; the '
                 'safeguard is not built, returning identity')
-    if self.use_icp:
-      raise NotImplementedError('ICP refinement (open3d, core/deep_global_registration.py:317-322) is a '
-                                '"next" row of the build plan and is not built')
+    if self.use_icp and self.last_branch == 'procrustes':
+      icp = host[17:37]
+      T = icp[:16].reshape(4, 4).copy()
+      self.last_info.update(icp_fitness=float(icp[16]), icp_inlier_rmse=float(icp[17]),
+                            icp_iterations=int(icp[18]))
     return T

@@ -224,6 +224,20 @@ int32_t dgr_se3_register(const float* x, const float* y, const int32_t* idx1, co
                          int32_t max_break_count, float break_threshold_ratio, float lr, float gamma,
                          float* pack_ws, int32_t* cnt_ws, float* result, void* stream);
 
+/* ---- ICP fine-tune: open3d registration_icp point-to-point with default
+ *      criteria (core/deep_global_registration.py:317-322) --------------------------------- */
+/* Nearest target point within max_dist through the TARGET cloud's voxel hash (keys / vals / spec
+ * of the table dgr_unique_first built at `voxel`; table rows = rows of tgt; `batch` = the batch
+ * index those coordinates carry), Kabsch update in fp64, stop when fitness and inlier RMSE both
+ * change by less than the tolerances or after max_iter updates.  No host round trip.
+ * T_init: device double[12] row-major [R | t]; state_ws: 64 doubles; result: device double[20] =
+ * 4x4 pose, fitness, inlier rmse, iterations, correspondences. */
+int32_t dgr_icp_point_to_point(const float* src, int64_t n_src, const float* tgt, const dgr_keyspec_t* spec,
+                               const uint64_t* keys, const int32_t* vals, int64_t cap, int32_t batch,
+                               double voxel, double max_dist, const double* T_init, int32_t max_iter,
+                               double rel_fitness, double rel_rmse, double* state_ws, double* result,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,7 +50,7 @@ def inlier_logits(state, coords6, feats):
                          False)
 
 
-def register(state, xyz0, xyz1, clip_weight_thresh=0.05):
+def register(state, xyz0, xyz1, clip_weight_thresh=0.05, use_icp=False):
   """Returns (T 4x4 float64, taps dict).  T is identity when the weight-sum gate
   (:276-281) sends the pair to the safeguard branch, which is not part of the
   built path; taps['branch'] says which branch was taken."""
@@ -71,7 +71,11 @@ def register(state, xyz0, xyz1, clip_weight_thresh=0.05):
     R, t, info = se3_refine(p0, p1[idx1], w, 2 * vs)
     T[:3, :3] = R.numpy()
     T[:3, 3] = t.numpy().reshape(3)
-    taps.update(branch='procrustes', refine=info)
+    taps.update(branch='procrustes', refine=info, T_refined=T.copy())
+    if use_icp:      # :317-322
+      from .icp import icp_point_to_point
+      T, icp_info = icp_point_to_point(p0, p1, 2 * vs, T)
+      taps.update(icp=icp_info)
   else:
     taps.update(branch='safeguard')
   return T, taps

@@ -27,7 +27,10 @@ def state():
 def dgr(state):
   from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
   cfg = types.SimpleNamespace(weights=state, clip_weight_thresh=0.05, verbose=False)
-  return DeepGlobalRegistration(cfg, device=torch.device('cuda'))
+  d = DeepGlobalRegistration(cfg, device=torch.device('cuda'))
+  assert d.use_icp is True           # reference default
+  d.use_icp = False                  # these tests compare the pre-ICP pose ("tap A") unless stated
+  return d
 
 
 def _rel(got, want):
@@ -87,6 +90,7 @@ def test_register_known_answer_rigid_copy():
   st = syn.make_checkpoint(4, voxel_size=vs)
   cfg = types.SimpleNamespace(weights=st, clip_weight_thresh=0.05, verbose=False)
   d = DeepGlobalRegistration(cfg)
+  d.use_icp = False
   xyz0 = syn.room_scan(2, 20000, EXTENT, scene_seed=1)
   T_gt = np.eye(4)
   shift = np.array([8, -16, 24])
@@ -126,6 +130,7 @@ def test_register_float32_and_lidar_shape(dgr, state):
   st = syn.make_checkpoint(3, voxel_size=0.3, feat_conv1_kernel_size=5)
   cfg = types.SimpleNamespace(weights=st, clip_weight_thresh=0.05, verbose=False)
   d = DeepGlobalRegistration(cfg)
+  d.use_icp = False
   xyz0, xyz1, _ = syn.lidar_pair(0)
   xyz0, xyz1 = xyz0[::4].astype(np.float32), xyz1[::4].astype(np.float32)
   with torch.no_grad():
@@ -179,12 +184,47 @@ def test_preprocess_rejects_unknown_input(dgr):
 
 
 def test_unbuilt_stages_fail_loudly(dgr):
-  xyz0, xyz1, _ = syn.room_pair(6, n_raw=4000, extent=(1.0, 1.0, 0.8))
-  dgr.use_icp = True
-  try:
-    with pytest.raises(NotImplementedError):
-      dgr.register(xyz0, xyz1)
-  finally:
-    dgr.use_icp = False
   with pytest.raises(NotImplementedError):
     dgr.safeguard_registration()
+
+
+def test_icp_kernel_vs_oracle():
+  """dgr_icp_point_to_point against the open3d restatement (oracle/icp.py): same pose to 1e-6,
+  same fitness / RMSE / iteration count, from a perturbed initial pose."""
+  from deepglobalregistration_b200 import _abi
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+  from oracle.icp import icp_point_to_point
+  st = syn.make_checkpoint(0, with_inlier=True)
+  d = DeepGlobalRegistration(types.SimpleNamespace(weights=st, clip_weight_thresh=0.05, verbose=False))
+  g = np.random.default_rng(0)
+  xyz0 = syn.room_scan(3, 30000, EXTENT)
+  T_gt = syn.random_se3(g, 20.0, 0.3)
+  xyz1 = syn.apply_se3(T_gt, syn.room_scan(4, 30000, EXTENT, scene_seed=3))
+  with torch.no_grad():
+    p0, c0, _ = d.preprocess(xyz0, 0, _batch=0)
+    p1, c1, _ = d.preprocess(xyz1, 1, _batch=1)
+  for trial, (ang, tr) in enumerate(((0.0, 0.0), (2.0, 0.03), (6.0, 0.08))):
+    T_init = syn.random_se3(np.random.default_rng(10 + trial), ang, tr) @ T_gt if ang else T_gt.copy()
+    res = _abi.icp_point_to_point(p0, p1, c1._dgr_manager, 0.05, 0.1, T_init, batch=1).cpu().numpy()
+    T_o, info = icp_point_to_point(p0.cpu().numpy(), p1.cpu().numpy(), 0.1, T_init)
+    te, re = syn.rte_rre(res[:16].reshape(4, 4), T_o)
+    assert te <= 1e-5 and re <= 1e-5, (trial, te, re, res[16:], info)
+    assert abs(res[16] - info['fitness']) <= 2e-4 and abs(res[17] - info['inlier_rmse']) <= 1e-5
+    assert abs(int(res[18]) - info['iterations']) <= 1, (res[18], info)
+  # the refined pose gets closer to the ground truth than the perturbed start
+  te_i, re_i = syn.rte_rre(T_init, T_gt)
+  te_f, re_f = syn.rte_rre(res[:16].reshape(4, 4), T_gt)
+  assert te_f < te_i and re_f < re_i
+
+
+def test_register_with_icp_vs_oracle(state):
+  """Tap B: the literal return value of the reference's register() (use_icp = True)."""
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+  d = DeepGlobalRegistration(types.SimpleNamespace(weights=state, clip_weight_thresh=0.05, verbose=False))
+  xyz0, xyz1, _ = syn.room_pair(2, n_raw=20000, extent=EXTENT)
+  T = d.register(xyz0, xyz1)
+  T_o, taps = op.register(state, xyz0, xyz1, use_icp=True)
+  assert d.last_branch == taps['branch'] == 'procrustes'
+  te, re = syn.rte_rre(T, T_o)
+  assert te <= 1e-3 and re <= 1e-3, (te, re, d.last_info, taps['icp'])
+  assert abs(d.last_info['icp_fitness'] - taps['icp']['fitness']) <= 5e-3

@@ -30,6 +30,7 @@ def ev():
 def config3():
   st = syn.make_checkpoint(3, voxel_size=0.3, feat_conv1_kernel_size=5)
   d = DeepGlobalRegistration(types.SimpleNamespace(weights=st, clip_weight_thresh=0.05, verbose=False))
+  d.use_icp = False
   xyz0, xyz1, T = syn.lidar_pair(0)
   xyz0, xyz1 = xyz0.astype(np.float32), xyz1.astype(np.float32)      # KITTI .bin is float32
   for _ in range(5):
