@@ -147,6 +147,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU baseline (oracle port) - also the --impl reference arm
 # ------------------------------------------------------------------------------------------
+def cgroup_throttled_ms():
+  """Cumulative time this container's CPU cgroup has been throttled (ms), or None."""
+  for path in ('/sys/fs/cgroup/cpu.stat', '/sys/fs/cgroup/cpu/cpu.stat'):
+    try:
+      for line in open(path):
+        k, v = line.split()
+        if k == 'throttled_usec':
+          return int(v) / 1e3
+        if k == 'throttled_time':
+          return int(v) / 1e6
+    except Exception:   # noqa: BLE001
+      continue
+  return None
+
+
 def effective_cpus():
   """Host threads this process may really use: affinity mask and cgroup CPU quota, not nproc."""
   n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
@@ -294,7 +309,7 @@ def run_ours(args):
     return dict(ms=ms, wall=wall, launches=launches, d2h=d2h, prof=prof, poses=gathered, steps_ms=steps_ms)
 
   # started before the warm-up: nvidia-smi's own start-up (NVML init) must not land in the timed region
-  sampler = ClockSampler(local) if rank == 0 else None
+  sampler = ClockSampler(local) if rank == 0 and not os.environ.get('DGR_BENCH_NO_SAMPLER') else None
   log(f'[bench] rank {rank}/{world}: model + {POOL} pairs ready, warming up')
   # warm-up: every pair of the pool at least max(W, 3) times on both input paths, so that the
   # caching allocator has seen every buffer size before anything is timed
@@ -310,10 +325,12 @@ def run_ours(args):
   log('[bench] warm-up done, timing')
 
   t_start = time.time()
+  thr0 = cgroup_throttled_ms()
   res = timed(args.steps, host_inputs=False, profile=True)     # `value`: scans resident in HBM
   t_mid = time.time()
   res_e2e = timed(args.steps, host_inputs=True)                 # `e2e`: host buffers in, pose out
   t_end = time.time()
+  thr1 = cgroup_throttled_ms()
   clocks = sampler.stop(t_start, t_end) if sampler else None
 
   if rank != 0:
@@ -384,10 +401,12 @@ def run_ours(args):
           'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor,
           'kernel_share_of_step': kernel_share, 'cpu_baseline': cpu,
           'wall_ms_per_step': 1e3 * res['wall'] / K,
+          'host_cgroup_throttled_ms_during_timing': (thr1 - thr0) if thr0 is not None and thr1 is not None else None,
+          'host_threads': {'torch_intraop': torch.get_num_threads(), 'usable_cpus': effective_cpus()},
           'step_ms': {'min': min(res['steps_ms']), 'median': float(np.median(res['steps_ms'])),
-                      'max': max(res['steps_ms'])},
+                      'max': max(res['steps_ms']), 'all': [round(x, 2) for x in res['steps_ms']]},
           'e2e_step_ms': {'min': min(res_e2e['steps_ms']), 'median': float(np.median(res_e2e['steps_ms'])),
-                          'max': max(res_e2e['steps_ms'])},
+                          'max': max(res_e2e['steps_ms']), 'all': [round(x, 2) for x in res_e2e['steps_ms']]},
           'published_reference': '0.69 s/pair without safeguard+ICP (reference assets/results.npz, unknown GPU)'}
   _emit(json.dumps(line))
   if world > 1:
@@ -402,10 +421,14 @@ def main():
   _emit = lambda text: os.write(real_stdout, (text + '\n').encode())
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=None,
+                  help='timed steps (default 100 for the B200 arm: ~1.5 s per region, so that one ~0.3 s host stall '
+                       'of a shared box costs 10-20 %% instead of halving the number; 10 for --impl reference)')
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   args = ap.parse_args()
+  if args.steps is None:
+    args.steps = 10 if args.impl == 'reference' else 100
   if args.impl == 'reference':
     run_reference(args)
   else:
