@@ -46,11 +46,11 @@ SIGNATURES = {
     'dgr_kmap_ws_elems': [_i32, _i64],
     'dgr_kernel_map_count': [_p, _i32, _i64, _p, _i32, _p, _p, _p],
     'dgr_kernel_map_fill': [_p, _i32, _i64, _p, _p, _p, _p],
-    'dgr_kernel_map_tiles': [_p, _i32, _i32, _i32, _p, _p, _p],
+    'dgr_kernel_map_tiles': [_p, _i32, _i32, _i32, _i32, _p, _p, _p],
     'dgr_spconv_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
     'dgr_spconv_tc_supported': [_i32, _i32],
     'dgr_pack_weight_tf32': [_p, _i32, _i32, _i32, _p, _p],
-    'dgr_spconv_tc_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
+    'dgr_spconv_tc_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p],
     'dgr_spconv_table_fwd': [_p, _i32, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p],
     'dgr_linear_fwd': [_p, _i32, _p, _i32, _i64, _p, _i32, _p, _i32, _i32, _p, _p],
     'dgr_affine_act': [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p],
@@ -275,12 +275,25 @@ def stride_coords(coords, out_stride):
 class KernelMap:
   """Neighbour table + (kappa, j)-sorted pair lists + the gather-GEMM-scatter work list."""
   __slots__ = ('K', 'n_in', 'n_out', 'nbr', 'in_idx', 'out_idx', 'kofs', 'kofs_host', 'n_pairs',
-               'tile_k', 'tile_start', 'n_tiles')
+               'tile_k', 'tile_start', 'n_tiles', '_paired')
+
+  def paired_tiles(self):
+    """(tile_k, tile_start, n_tiles) with an even tile count per offset (2-CTA cluster kernel)."""
+    if getattr(self, '_paired', None) is None:
+      counts = self.kofs_host[1:] - self.kofs_host[:-1]
+      per_k = (counts + TILE_ROWS - 1) // TILE_ROWS
+      n = int(((per_k + 1) // 2 * 2).sum())
+      dev = self.kofs.device
+      tk = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+      ts = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+      call('dgr_kernel_map_tiles', ptr(self.kofs), self.K, TILE_ROWS, n, 1, ptr(tk), ptr(ts), stream())
+      self._paired = (tk, ts, n)
+    return self._paired
 
   def transposed(self):
     t = KernelMap()
     for k in self.__slots__:
-      setattr(t, k, getattr(self, k))
+      setattr(t, k, getattr(self, k, None))
     t.in_idx, t.out_idx = self.out_idx, self.in_idx
     t.n_in, t.n_out = self.n_out, self.n_in
     t.nbr = None
@@ -322,9 +335,10 @@ def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
     call('dgr_kernel_map_fill', ptr(nbr), K, n_out, ptr(ws), ptr(km.in_idx), ptr(km.out_idx), stream())
   km.tile_k = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
   km.tile_start = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
-  call('dgr_kernel_map_tiles', ptr(kofs), K, TILE_ROWS, n_tiles, ptr(km.tile_k), ptr(km.tile_start), stream())
+  call('dgr_kernel_map_tiles', ptr(kofs), K, TILE_ROWS, n_tiles, 0, ptr(km.tile_k), ptr(km.tile_start), stream())
   km.kofs, km.kofs_host, km.n_pairs, km.n_tiles = kofs, kofs_host, P, n_tiles
   km.nbr = nbr if keep_table else None
+  km._paired = None
   return km
 
 
@@ -353,6 +367,12 @@ def pack_weight_tf32(weight, K, cin, cout):
   return packed
 
 
+# kernel variant of the tensor-core convolution: 1 = both operands in shared memory (default,
+# fastest measured), 0 = A operand in tensor memory, 2 = 1 with CTA pairs and multicast weight
+# tiles.  All three are parity-tested; all three run at the same speed on the wide layers, which
+# is how the L2->SM ingress bound was identified.
+TC_VARIANT = int(os.environ.get('DGR_TC_VARIANT', '1'))
+
 # When set to a list, every sparse-convolution launch appends
 # (kernel name, start event, end event, algorithmic flops, gather-scatter-model bytes):
 # bench.py's live per-kernel roofline measurement (CUDA events on the launching stream).
@@ -374,16 +394,21 @@ def _conv_profiled(name, km, cin, cout, fn):
   CONV_PROFILE.append((name, e0, e1, flops, nbytes))
 
 
-def spconv_tc_fwd(feat, weight_t, km, out, passes=3):
+def spconv_tc_fwd(feat, weight_t, km, out, passes=3, cluster=None):
   """Tensor-core gather-GEMM-scatter: out[km.out_idx] += feat[km.in_idx] @ W[kappa]."""
   _chk(feat, torch.float32, 'feat'); _chk(weight_t, torch.float32, 'weight_t'); _chk(out, torch.float32, 'out')
   cin, cout = feat.shape[1], out.shape[1]
   assert weight_t.numel() == 2 * km.K * cin * cout
   assert feat.shape[0] == km.n_in and out.shape[0] == km.n_out
+  if cluster is None:
+    cluster = TC_VARIANT
+  if cluster == 2:
+    tk, ts, nt = km.paired_tiles()
+  else:
+    tk, ts, nt = km.tile_k, km.tile_start, km.n_tiles
   _conv_profiled('spconv_tc_kernel', km, cin, cout, lambda: call(
       'dgr_spconv_tc_fwd', ptr(feat), cin, ptr(weight_t), cout, ptr(km.in_idx), ptr(km.out_idx),
-      ptr(km.kofs), ptr(km.tile_k), ptr(km.tile_start), km.n_tiles, TILE_ROWS, int(passes), ptr(out),
-      stream()))
+      ptr(km.kofs), ptr(tk), ptr(ts), nt, TILE_ROWS, int(passes), cluster, ptr(out), stream()))
   return out
 
 

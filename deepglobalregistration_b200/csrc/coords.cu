@@ -383,7 +383,7 @@ __global__ void kernel_map_fill_kernel(const int32_t* __restrict__ nbr, int64_t 
   }
 }
 
-__global__ void tiles_kernel(const int32_t* __restrict__ kofs, int K, int tile_rows, int n_tiles,
+__global__ void tiles_kernel(const int32_t* __restrict__ kofs, int K, int tile_rows, int n_tiles, int pair,
                              int32_t* __restrict__ tile_k, int32_t* __restrict__ tile_start) {
   extern __shared__ int tofs[];   // K + 1 exclusive tile offsets
   __shared__ int wsum[32];
@@ -393,7 +393,8 @@ __global__ void tiles_kernel(const int32_t* __restrict__ kofs, int K, int tile_r
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = 0; base < K; base += blockDim.x) {   // block-wide scan, 1024 buckets per round
     const int k = base + threadIdx.x;
-    const int v = k < K ? (kofs[k + 1] - kofs[k] + tile_rows - 1) / tile_rows : 0;
+    int v = k < K ? (kofs[k + 1] - kofs[k] + tile_rows - 1) / tile_rows : 0;
+    if (pair) v = (v + 1) & ~1;     // CTA pairs: an even number of tiles per offset (last one may be empty)
     int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -609,11 +610,11 @@ int32_t dgr_kernel_map_fill(const int32_t* nbr, int32_t K, int64_t n_out, const 
   return DGR_OK;
 }
 
-int32_t dgr_kernel_map_tiles(const int32_t* kofs, int32_t K, int32_t tile_rows, int32_t n_tiles,
+int32_t dgr_kernel_map_tiles(const int32_t* kofs, int32_t K, int32_t tile_rows, int32_t n_tiles, int32_t pair,
                              int32_t* tile_k, int32_t* tile_start, void* stream) {
   DGR_ARG_CHECK(tile_rows >= 1, "tile_rows must be positive");
   if (n_tiles == 0) return DGR_OK;
-  tiles_kernel<<<1, 1024, (K + 1) * sizeof(int), (cudaStream_t)stream>>>(kofs, K, tile_rows, n_tiles,
+  tiles_kernel<<<1, 1024, (K + 1) * sizeof(int), (cudaStream_t)stream>>>(kofs, K, tile_rows, n_tiles, pair,
                                                                         tile_k, tile_start);
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();

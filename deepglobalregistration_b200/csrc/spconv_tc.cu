@@ -49,6 +49,30 @@ __device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, un
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy delivered to the same CTA-relative offsets of every CTA in `mask`; each destination's
+// mbarrier (same offset) receives the complete_tx of the bytes written into that CTA
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                                   uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -76,6 +100,7 @@ struct TcShared {
 // (tile = blockIdx.x + i * gridDim.x) and meet only through mbarriers:
 //   loaders  --full[s]-->  MMA issuer  --empty[s]-->  loaders        (shared-memory stages)
 //   MMA issuer  --acc_full[b]-->  epilogue  --acc_empty[b]-->  MMA   (two TMEM accumulators)
+template <int kCluster>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __restrict__ wt, int cout,
                  const int32_t* __restrict__ in_idx, const int32_t* __restrict__ out_idx,
@@ -98,7 +123,7 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(smem_u32(&sh.full[s]), kLoaderThreads);
       mbar_init(smem_u32(&sh.full_lo[s]), 1);
-      mbar_init(smem_u32(&sh.empty[s]), 1);
+      mbar_init(smem_u32(&sh.empty[s]), kCluster);   // one tcgen05.commit per CTA that reads the stage's B
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&sh.acc_full[b]), 1);
@@ -115,8 +140,10 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts
   tc_fence_after();
   const uint32_t tmem_base = sh.tmem_base;
+  const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
 
   if (warp < kLoaderWarps) {
     // ================================ loaders ============================================
@@ -168,10 +195,20 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
           // own barrier while those products already run
           const float* src = slab + (size_t)c * (slab_bytes / 4);
           mbar_expect_tx(smem_u32(&sh.full[s]), (uint32_t)b_tile_bytes);
-          bulk_g2s(smem_u32(a_lo + kATileBytes), src, (uint32_t)b_tile_bytes, smem_u32(&sh.full[s]));
           mbar_arrive_expect_tx(smem_u32(&sh.full_lo[s]), (uint32_t)b_tile_bytes);
-          bulk_g2s(smem_u32(a_lo + kATileBytes + b_tile_bytes), src + b_tile_bytes / 4, (uint32_t)b_tile_bytes,
-                   smem_u32(&sh.full_lo[s]));
+          if (kCluster == 1) {
+            bulk_g2s(smem_u32(a_lo + kATileBytes), src, (uint32_t)b_tile_bytes, smem_u32(&sh.full[s]));
+            bulk_g2s(smem_u32(a_lo + kATileBytes + b_tile_bytes), src + b_tile_bytes / 4, (uint32_t)b_tile_bytes,
+                     smem_u32(&sh.full_lo[s]));
+          } else if (cta_rank == 0) {
+            // the CTA pair works on two tiles of the SAME offset: one L2 read of each B tile feeds both
+            // SMs - rank 0 multicasts the hi tile, rank 1 the lo tile (empty[s] counts both CTAs' MMAs)
+            bulk_g2s_multicast(smem_u32(a_lo + kATileBytes), src, (uint32_t)b_tile_bytes, smem_u32(&sh.full[s]),
+                               (uint16_t)0x3);
+          } else {
+            bulk_g2s_multicast(smem_u32(a_lo + kATileBytes + b_tile_bytes), src + b_tile_bytes / 4,
+                               (uint32_t)b_tile_bytes, smem_u32(&sh.full_lo[s]), (uint16_t)0x3);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) split_store(a_cur[i], a_hi, a_lo, a_off + i * 4096);
@@ -221,7 +258,8 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
             for (int ks = 0; ks < kChunk / 8; ++ks)
               tc_mma_tf32(tmem_d, umma_desc(a_hi + ks * 32), umma_desc(b_lo + ks * 32), idesc, 1);
           }
-          tc_commit(smem_u32(&sh.empty[s]));
+          if (kCluster == 1) tc_commit(smem_u32(&sh.empty[s]));
+          else tc_commit_multicast(smem_u32(&sh.empty[s]), (uint16_t)0x3);   // frees the stage in both CTAs
           if (c == n_chunks - 1) tc_commit(smem_u32(&sh.acc_full[buf]));
         }
         __syncwarp();
@@ -254,6 +292,213 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
         }
       }
       if (col < cout) {   // cout % 32 == 16
+        uint32_t v[16];
+        tc_ld16(taddr + col, v);
+        if (j >= 0) {
+          float* dst = out + (size_t)j * cout + col;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh.acc_empty[buf]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();     // nobody exits while a peer may still signal its barriers
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Variant with the A operand in TENSOR MEMORY.
+// With both operands in shared memory every one of the three TF32 products re-reads A and B
+// from shared memory: 12 MMAs x 12 KB + 96 KB of stores per 32-channel chunk = 240 KB against a
+// 128 B/clk port - the SS kernel above is shared-memory-bandwidth bound (ncu: tensor pipe 55 %).
+// Here the loaders put the split A tiles straight into TMEM (tcgen05.st; thread = row = lane),
+// the MMAs read only B from shared memory (96 KB per chunk) and shared memory holds nothing but
+// the bulk-copied weight slabs, which also makes room for deeper pipelines.
+// TMEM columns: [accumulator(s)] [stage 0: A hi (32) | A lo (32)] [stage 1 ...].
+// Loader warps 0-3 fill even chunks, warps 4-7 odd chunks (warp w owns TMEM lanes 32 (w % 4) ..).
+// ---------------------------------------------------------------------------------------
+struct TcAtShared {
+  unsigned long long full[4];      // 128 loader arrivals (A in TMEM) + B hi bytes
+  unsigned long long full_lo[4];   // B lo bytes
+  unsigned long long empty[4];
+  unsigned long long acc_full[2];
+  unsigned long long acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreadsTC, 1)
+spconv_tc_at_kernel(const float* __restrict__ in_feat, int cin, const float* __restrict__ wt, int cout,
+                    const int32_t* __restrict__ in_idx, const int32_t* __restrict__ out_idx,
+                    const int32_t* __restrict__ kofs, const int32_t* __restrict__ tile_k,
+                    const int32_t* __restrict__ tile_start, int n_tiles, int n_stages, int tmem_cols,
+                    int n_acc, int acc_cols, int passes, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  TcAtShared& sh = *reinterpret_cast<TcAtShared*>(smem_dyn);
+  unsigned char* stage0 = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + sizeof(TcAtShared) + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = cout * 128;
+  const int stage_bytes = 2 * b_tile_bytes;          // shared memory holds only [B hi | B lo]
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int n_chunks = cin / kChunk;
+  const uint32_t a_col0 = (uint32_t)(n_acc * acc_cols);   // first column of the A stages
+
+  if (t == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(smem_u32(&sh.full[s]), 128);
+      mbar_init(smem_u32(&sh.full_lo[s]), 1);
+      mbar_init(smem_u32(&sh.empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&sh.acc_full[b]), 1);
+      mbar_init(smem_u32(&sh.acc_empty[b]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&sh.tmem_base)),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_base;
+
+  if (warp < kLoaderWarps) {
+    // ================================ loaders ============================================
+    const int group = warp >> 2;                       // 0: even chunks, 1: odd chunks
+    const int row = (warp & 3) * 32 + lane;            // tile row == TMEM lane of this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const bool issuer = (t == group * 128);            // one bulk-copy issuer per group
+    const uint32_t slab_bytes = 2u * (uint32_t)b_tile_bytes;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int kappa = tile_k[tile];
+      const int p0 = tile_start[tile];
+      const int rows = min(kTileM, kofs[kappa + 1] - p0);
+      const int src = row < rows ? __ldg(in_idx + p0 + row) : -1;
+      const float4* src_row = reinterpret_cast<const float4*>(in_feat + (size_t)(src < 0 ? 0 : src) * cin);
+      const float* slab = wt + (size_t)kappa * n_chunks * (slab_bytes / 4);
+      for (int c = 0; c < n_chunks; ++c, ++it) {
+        if ((int)(it & 1) != group) continue;
+        const int s = it % n_stages;
+        const uint32_t ph = (it / n_stages) & 1;
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          v[q] = src >= 0 ? __ldg(src_row + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(smem_u32(&sh.empty[s]), ph ^ 1);
+        tc_fence_after();
+        if (issuer) {
+          const float* bsrc = slab + (size_t)c * (slab_bytes / 4);
+          unsigned char* b_hi = stage0 + (size_t)s * stage_bytes;
+          mbar_expect_tx(smem_u32(&sh.full[s]), (uint32_t)b_tile_bytes);
+          bulk_g2s(smem_u32(b_hi), bsrc, (uint32_t)b_tile_bytes, smem_u32(&sh.full[s]));
+          mbar_arrive_expect_tx(smem_u32(&sh.full_lo[s]), (uint32_t)b_tile_bytes);
+          bulk_g2s(smem_u32(b_hi + b_tile_bytes), bsrc + b_tile_bytes / 4, (uint32_t)b_tile_bytes,
+                   smem_u32(&sh.full_lo[s]));
+        }
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float f[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float h = tf32_round(f[e]);
+            hi[4 * q + e] = __float_as_uint(h);
+            lo[4 * q + e] = __float_as_uint(f[e] - h);
+          }
+        }
+        const uint32_t a_addr = lane_addr + a_col0 + (uint32_t)s * 64;
+        tc_st32(a_addr, hi);
+        tc_st32(a_addr + 32, lo);
+        tc_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&sh.full[s]));
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================ MMA issuer =========================================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cout >> 3) << 17) |
+                           ((uint32_t)(kTileM >> 4) << 24);
+    uint32_t it = 0, tile_iter = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+      const uint32_t buf = n_acc == 2 ? (tile_iter & 1) : 0;
+      const uint32_t use = n_acc == 2 ? (tile_iter >> 1) : tile_iter;     // uses of this accumulator so far
+      const uint32_t tmem_d = tmem_base + buf * (uint32_t)acc_cols;
+      mbar_wait(smem_u32(&sh.acc_empty[buf]), (use & 1) ^ 1);
+      tc_fence_after();
+      for (int c = 0; c < n_chunks; ++c, ++it) {
+        const int s = it % n_stages;
+        const uint32_t ph = (it / n_stages) & 1;
+        const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)s * 64, a_lo = a_hi + 32;
+        const uint32_t b_hi = smem_u32(stage0 + (size_t)s * stage_bytes), b_lo = b_hi + b_tile_bytes;
+        mbar_wait(smem_u32(&sh.full[s]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < kChunk / 8; ++ks) {
+            const uint64_t dbh = umma_desc(b_hi + ks * 32);
+            tc_mma_tf32_ts(tmem_d, a_hi + ks * 8, dbh, idesc, (c | ks) != 0);
+            if (passes == 3) tc_mma_tf32_ts(tmem_d, a_lo + ks * 8, dbh, idesc, 1);
+          }
+        }
+        mbar_wait(smem_u32(&sh.full_lo[s]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          if (passes == 3) {
+#pragma unroll
+            for (int ks = 0; ks < kChunk / 8; ++ks)
+              tc_mma_tf32_ts(tmem_d, a_hi + ks * 8, umma_desc(b_lo + ks * 32), idesc, 1);
+          }
+          tc_commit(smem_u32(&sh.empty[s]));
+          if (c == n_chunks - 1) tc_commit(smem_u32(&sh.acc_full[buf]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue ===========================================
+    const int lane_grp = warp & 3;
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+      const uint32_t buf = n_acc == 2 ? (tile_iter & 1) : 0;
+      const uint32_t use = n_acc == 2 ? (tile_iter >> 1) : tile_iter;
+      const int kappa = tile_k[tile];
+      const int p0 = tile_start[tile];
+      const int rows = min(kTileM, kofs[kappa + 1] - p0);
+      const int r = lane_grp * 32 + lane;
+      const int j = r < rows ? out_idx[p0 + r] : -1;
+      mbar_wait(smem_u32(&sh.acc_full[buf]), use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * (uint32_t)acc_cols + ((uint32_t)(lane_grp * 32) << 16);
+      int col = 0;
+      for (; col + 32 <= cout; col += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + col, v);
+        if (j >= 0) {
+          float* dst = out + (size_t)j * cout + col;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      if (col < cout) {
         uint32_t v[16];
         tc_ld16(taddr + col, v);
         if (j >= 0) {
@@ -327,10 +572,11 @@ int32_t dgr_spconv_tc_supported(int32_t cin, int32_t cout) {
 int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight_t, int32_t cout,
                           const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,
                           const int32_t* tile_k, const int32_t* tile_start, int32_t n_tiles,
-                          int32_t tile_rows, int32_t passes, float* out, void* stream) {
+                          int32_t tile_rows, int32_t passes, int32_t cluster, float* out, void* stream) {
   DGR_ARG_CHECK(tile_rows == kTileM, "tile_rows must be 128");
   DGR_ARG_CHECK(dgr_spconv_tc_supported(cin, cout), "shape not supported by the tensor-core path");
   DGR_ARG_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
+  DGR_ARG_CHECK(cluster >= 0 && cluster <= 2, "variant must be 0 (A in TMEM), 1 (A in smem) or 2 (CTA pairs)");
   if (n_tiles == 0) return DGR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int stage_bytes = 2 * kATileBytes + 2 * cout * 128;
@@ -342,17 +588,56 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
   int acc_cols = 32;                       // one accumulator: power of two >= cout
   while (acc_cols < cout) acc_cols <<= 1;
   const int tmem_cols = 2 * acc_cols;      // two accumulators: epilogue overlaps the next tile
-  DGR_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
   int dev = 0, sms = 148;
   DGR_CUDA_CHECK(cudaGetDevice(&dev));
   DGR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   (void)n_chunks;
   int grid = sms;                          // persistent: one warp-specialised CTA per SM
   if (grid > n_tiles) grid = n_tiles;
-  spconv_tc_kernel<<<grid, kThreadsTC, smem, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
-                                                   tile_k, tile_start, n_tiles, n_stages, tmem_cols, passes,
-                                                   out);
+  if (cluster == 0) {
+    // A operand in tensor memory: shared memory holds only the weight slabs
+    const int sb = 2 * cout * 128;
+    int ns = (200 * 1024) / sb;
+    if (ns > 4) ns = 4;
+    int n_acc = 2;
+    if (2 * acc_cols + 64 * 2 > 512) n_acc = 1;            // cout > 128: one accumulator
+    while (ns > 2 && n_acc * acc_cols + 64 * ns > 512) --ns;
+    int cols = 32;
+    while (cols < n_acc * acc_cols + 64 * ns) cols <<= 1;
+    const size_t smem_at = sizeof(TcAtShared) + 1024 + (size_t)ns * sb;
+    DGR_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_at_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_at));
+    spconv_tc_at_kernel<<<grid, kThreadsTC, smem_at, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
+                                                           tile_k, tile_start, n_tiles, ns, cols, n_acc, acc_cols,
+                                                           passes, out);
+  } else if (cluster == 2) {
+    // CTA pairs on two tiles of the same offset, B tiles multicast to both (paired tile list)
+    DGR_ARG_CHECK(n_tiles % 2 == 0, "a paired tile list has an even number of tiles");
+    grid &= ~1;
+    DGR_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreadsTC);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DGR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<2>, in_feat, (int)cin, weight_t, (int)cout, in_idx,
+                                      out_idx, kofs, tile_k, tile_start, (int)n_tiles, n_stages, tmem_cols,
+                                      (int)passes, out));
+  } else {
+    DGR_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    spconv_tc_kernel<1><<<grid, kThreadsTC, smem, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
+                                                        tile_k, tile_start, n_tiles, n_stages, tmem_cols, passes,
+                                                        out);
+  }
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;

@@ -132,8 +132,10 @@ int32_t dgr_kernel_map_fill(const int32_t* nbr, int32_t K, int64_t n_out, const 
                             int32_t* in_idx, int32_t* out_idx, void* stream);
 /* Work list of the gather-GEMM-scatter kernel: tile t covers pairs
  * [tile_start[t], min(tile_start[t] + tile_rows, kofs[tile_k[t] + 1])) of bucket tile_k[t].
- * n_tiles = sum_k ceil(count_k / tile_rows) is computed by the caller from kofs. */
-int32_t dgr_kernel_map_tiles(const int32_t* kofs, int32_t K, int32_t tile_rows, int32_t n_tiles,
+ * n_tiles = sum_k ceil(count_k / tile_rows) is computed by the caller from kofs.  pair != 0
+ * rounds every offset's tile count up to even (the extra tile is empty) - the list the 2-CTA
+ * cluster variant of the tensor-core convolution consumes. */
+int32_t dgr_kernel_map_tiles(const int32_t* kofs, int32_t K, int32_t tile_rows, int32_t n_tiles, int32_t pair,
                              int32_t* tile_k, int32_t* tile_start, void* stream);
 
 /* ---- sparse convolution forward: ME.MinkowskiConvolution / ConvolutionTranspose
@@ -154,13 +156,17 @@ int32_t dgr_spconv_fwd(const float* in_feat, int32_t cin, const float* weight, i
  * residual tile in shared-memory image order; the host caches it per layer; 2 * K * cin * cout
  * floats).  passes = 3 evaluates every
  * product as hi*hi + lo*hi + hi*lo on TF32 splits (fp32-accurate); passes = 1 is plain
- * TF32 (~1e-3 relative), offered as an opt-in fast mode. */
+ * TF32 (~1e-3 relative), offered as an opt-in fast mode.  `cluster` selects the kernel variant:
+ * 1 = both operands in shared memory (default); 0 = A operand split straight into tensor memory
+ * (tcgen05.st), shared memory holds only the weight slabs; 2 = as 1 with thread-block clusters of
+ * two CTAs that work on two tiles of the same offset and receive each weight tile by ONE multicast
+ * bulk copy (needs the paired tile list of dgr_kernel_map_tiles(pair = 1)). */
 int32_t dgr_spconv_tc_supported(int32_t cin, int32_t cout);
 int32_t dgr_pack_weight_tf32(const float* w, int32_t K, int32_t cin, int32_t cout, float* packed, void* stream);
 int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight_t, int32_t cout,
                           const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,
                           const int32_t* tile_k, const int32_t* tile_start, int32_t n_tiles,
-                          int32_t tile_rows, int32_t passes, float* out, void* stream);
+                          int32_t tile_rows, int32_t passes, int32_t cluster, float* out, void* stream);
 /* Output-stationary variant for few input channels (conv1: cin == 1): reads the dense
  * neighbour table, no atomics, optional fused per-channel affine (eval BatchNorm):
  *   out[j, :] = (sum_kappa in[nbr[kappa, j], :] @ W[kappa]) * scale + shift. */

@@ -108,6 +108,31 @@ def test_spconv_tensor_core(abi, D, cin, cout):
   _close(out2, init + 2 * want, what='tcgen05 accumulate')
 
 
+@pytest.mark.parametrize('D,cin,cout', [(3, 256, 256), (3, 128, 128), (6, 64, 240), (3, 32, 32)])
+def test_spconv_tensor_core_cta_pairs(abi, D, cin, cout):
+  """2-CTA cluster variant (weight tiles multicast to both CTAs, paired tile list with empty
+  padding tiles) must equal the single-CTA kernel's result."""
+  from deepglobalregistration_b200.me.coords import CoordinateManager, CoordinateMapKey
+  coords = _coords(cin + 7 * cout + D, 4000, D, 10 if D == 3 else 3)
+  n = len(coords)
+  g = torch.Generator().manual_seed(5)
+  feat = torch.randn(n, cin, generator=g)
+  W = torch.randn(3 ** D, cin, cout, generator=g) / np.sqrt(cin * 8)
+  man = CoordinateManager(torch.from_numpy(coords).cuda())
+  _, km = man.kernel_map(CoordinateMapKey(1), 1, 3)
+  want = so.conv_forward(feat, W, so.kernel_map(coords, coords, so.kernel_offsets(3, D, 1)), n)
+  Wt = abi.pack_weight_tf32(W.cuda().contiguous(), 3 ** D, cin, cout)
+  tk, ts, nt = km.paired_tiles()
+  assert nt % 2 == 0 and nt >= km.n_tiles
+  tkh = tk.cpu().numpy()[:nt]
+  assert (tkh[0::2] == tkh[1::2]).all()              # both tiles of a pair share the kernel offset
+  for variant, name in ((2, '2-CTA cluster'), (1, 'A in smem'), (0, 'A in TMEM')):
+    for rep in range(2):
+      out = torch.zeros(n, cout, device='cuda')
+      abi.spconv_tc_fwd(feat.cuda(), Wt, km, out, passes=3, cluster=variant)
+      _close(out, want, what=f'tcgen05 {name}')
+
+
 def test_tc_unsupported_shapes_fall_back(abi):
   assert not abi.tc_supported(1, 32) and not abi.tc_supported(48, 32) and not abi.tc_supported(32, 8)
   assert not abi.tc_supported(32, 264) and abi.tc_supported(64, 256)
