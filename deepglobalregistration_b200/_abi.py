@@ -300,28 +300,33 @@ class KernelMap:
     return t
 
 
-def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
-  """offsets: CUDA int32 [K, D] (scaled by the input tensor stride)."""
+def kernel_map_begin(out_coords, spec, in_table, n_in, offsets, keep_table=False, slot=0):
+  """First half of a kernel map: neighbour table + bucket counts, all asynchronous.  `slot` selects
+  the scratch buffers so that several maps can be in flight before ONE host read finishes them
+  all (kernel_maps_finish)."""
   _chk(out_coords, torch.int32, 'out_coords')
   _chk(offsets, torch.int32, 'offsets')
   dev = out_coords.device
   n_out, ncols = out_coords.shape
   K = offsets.shape[0]
-  km = KernelMap()
-  km.K, km.n_in, km.n_out = K, n_in, n_out
   if keep_table:
     nbr = torch.empty(K, max(n_out, 1), dtype=torch.int32, device=dev)
   else:
-    nbr = scratch('km_nbr', K * max(n_out, 1), torch.int32, dev).view(K, max(n_out, 1))
+    nbr = scratch(('km_nbr', slot), K * max(n_out, 1), torch.int32, dev).view(K, max(n_out, 1))
   # the miss filter pays off when most probes miss: many offsets per row (6-D, 5^3, 7^3 kernels)
   bloom, bloom_bits = in_table.bloom() if K > 27 else (None, 0)
-  ws = scratch('km_ws', lib().dgr_kmap_ws_elems(K, n_out), torch.int32, dev)
+  ws = scratch(('km_ws', slot), lib().dgr_kmap_ws_elems(K, n_out), torch.int32, dev)
   call('dgr_kernel_map_table', ptr(out_coords), n_out, ncols, ptr(spec), ptr(in_table.keys),
        ptr(in_table.vals), in_table.cap, ptr(bloom), bloom_bits, ptr(offsets), K, ptr(nbr), ptr(ws), stream())
   kofs = torch.empty(K + 2, dtype=torch.int32, device=dev)
   call('dgr_kernel_map_count', ptr(nbr), K, n_out, ptr(ws), 1, ptr(kofs), ptr(spec), stream())
-  kofs_all = kofs.cpu().numpy()           # the one host read of this map: P, tile count, key check
+  return dict(K=K, n_in=n_in, n_out=n_out, nbr=nbr, ws=ws, kofs=kofs, keep=keep_table, dev=dev)
+
+
+def kernel_map_finish(pend, kofs_all):
+  """Second half: pair lists and work list, sized from the host copy of the bucket offsets."""
   global D2H_BYTES
+  K, n_out, dev = pend['K'], pend['n_out'], pend['dev']
   D2H_BYTES += kofs_all.nbytes
   if kofs_all[K + 1] != 0:
     raise DgrError('coordinate extent does not fit a 63-bit packed key')
@@ -329,17 +334,40 @@ def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
   P = int(kofs_host[K])
   counts = kofs_host[1:] - kofs_host[:-1]
   n_tiles = int(((counts + TILE_ROWS - 1) // TILE_ROWS).sum())
+  km = KernelMap()
+  km.K, km.n_in, km.n_out = K, pend['n_in'], n_out
   km.in_idx = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
   km.out_idx = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
   if n_out > 0:
-    call('dgr_kernel_map_fill', ptr(nbr), K, n_out, ptr(ws), ptr(km.in_idx), ptr(km.out_idx), stream())
+    call('dgr_kernel_map_fill', ptr(pend['nbr']), K, n_out, ptr(pend['ws']), ptr(km.in_idx), ptr(km.out_idx),
+         stream())
   km.tile_k = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
   km.tile_start = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
-  call('dgr_kernel_map_tiles', ptr(kofs), K, TILE_ROWS, n_tiles, 0, ptr(km.tile_k), ptr(km.tile_start), stream())
-  km.kofs, km.kofs_host, km.n_pairs, km.n_tiles = kofs, kofs_host, P, n_tiles
-  km.nbr = nbr if keep_table else None
+  call('dgr_kernel_map_tiles', ptr(pend['kofs']), K, TILE_ROWS, n_tiles, 0, ptr(km.tile_k), ptr(km.tile_start),
+       stream())
+  km.kofs, km.kofs_host, km.n_pairs, km.n_tiles = pend['kofs'], kofs_host, P, n_tiles
+  km.nbr = pend['nbr'] if pend['keep'] else None
   km._paired = None
   return km
+
+
+def kernel_maps_finish(pending):
+  """Finish several begun kernel maps with a single device-to-host read."""
+  if not pending:
+    return []
+  host = torch.cat([p['kofs'] for p in pending]).cpu().numpy() if len(pending) > 1 else \
+      pending[0]['kofs'].cpu().numpy()
+  out, ofs = [], 0
+  for p in pending:
+    n = p['K'] + 2
+    out.append(kernel_map_finish(p, host[ofs:ofs + n]))
+    ofs += n
+  return out
+
+
+def kernel_map(out_coords, spec, in_table, n_in, offsets, keep_table=False):
+  """offsets: CUDA int32 [K, D] (scaled by the input tensor stride).  One host read."""
+  return kernel_maps_finish([kernel_map_begin(out_coords, spec, in_table, n_in, offsets, keep_table)])[0]
 
 
 def spconv_fwd(feat, weight, km, out, relu_in=False):

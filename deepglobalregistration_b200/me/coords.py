@@ -100,6 +100,40 @@ class CoordinateManager:
       self._maps[stride] = _Map(_abi.gather_rows_i32(floored, sel, n), table, n)
     return self._maps[stride]
 
+  def prepare(self, strides, maps):
+    """Build every missing coordinate map of `strides` and every missing kernel map of `maps`
+    ((s_in, conv_stride, kernel_size) triples) with TWO host reads in total instead of one per map:
+    all strided maps are derived from the stride-1 rows directly (floor(c / s) * s composes, and
+    ranking cells by their first stride-1 row reproduces the cascaded first-occurrence order), all
+    neighbour tables and bucket counts are enqueued before the single read that sizes them."""
+    base = self._maps[1]
+    todo = [s for s in strides if s not in self._maps]
+    if todo:
+      built = []
+      for s in todo:
+        floored = _abi.stride_coords(base.coords, s)
+        table, sel, _, cnt = _abi.unique_first(floored, self.spec)
+        built.append((s, floored, table, sel, cnt))
+      counts = torch.cat([b[4] for b in built]).cpu().tolist()
+      _abi.D2H_BYTES += 8 * len(built)
+      for i, (s, floored, table, sel, _) in enumerate(built):
+        n, overflow = counts[2 * i], counts[2 * i + 1]
+        if overflow:
+          raise _abi.DgrError('coordinate extent does not fit a 63-bit packed key')
+        self._maps[s] = _Map(_abi.gather_rows_i32(floored, sel, n), table, n)
+    pending, keys = [], []
+    for slot, (s_in, conv_stride, ksize) in enumerate(maps):
+      ck = (s_in, s_in * conv_stride, ksize)
+      if ck in self._kmaps or ck in keys:
+        continue
+      m_in, m_out = self._map(s_in), self._map(s_in * conv_stride)
+      keep = self.D == 3 and conv_stride == 1 and ksize > 3
+      pending.append(_abi.kernel_map_begin(m_out.coords, self.spec, m_in.table, m_in.n, self._offs(ksize, s_in),
+                                           keep_table=keep, slot=slot + 1))
+      keys.append(ck)
+    for ck, km in zip(keys, _abi.kernel_maps_finish(pending)):
+      self._kmaps[ck] = km
+
   def _offs(self, kernel_size, stride):
     k = (kernel_size, self.D, stride, self.device)
     if k not in _OFFSET_CACHE:          # process-wide: the offsets depend on nothing else

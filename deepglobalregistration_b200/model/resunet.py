@@ -138,6 +138,10 @@ class ResUNet2(ME.MinkowskiNetwork):
     host synchronisation of the forward pass happens (one bucket-offset read per map); the
     convolution phase that follows is launch-only.  Returns the layers in execution order as
     (conv module, norm module, kernel map, role) with the total size of their outputs."""
+    s0 = key.stride
+    man.prepare([2 * s0, 4 * s0, 8 * s0],
+                [(s0, 1, self.conv1.kernel_size), (s0, 1, 3), (s0, 2, 3), (2 * s0, 1, 3), (2 * s0, 2, 3),
+                 (4 * s0, 1, 3), (4 * s0, 2, 3), (8 * s0, 1, 3)])
     layers = []
     for l in (1, 2, 3, 4):
       cm = getattr(self, f'conv{l}')
