@@ -45,31 +45,31 @@ class DeepGlobalRegistration:
     self.voxel_size = network_config.voxel_size
     self._log(f'=> Setting voxel size to {self.voxel_size}')
 
-    num_feats = 1
-    try:
-      FCGFModel = load_model(network_config['feat_model'])
-      self.fcgf_model = FCGFModel(num_feats, network_config['feat_model_n_out'],
-                                  bn_momentum=network_config['bn_momentum'],
-                                  conv1_kernel_size=network_config['feat_conv1_kernel_size'],
-                                  normalize_feature=network_config['normalize_feature'])
-    except KeyError:                # legacy pretrained models
-      FCGFModel = load_model(network_config['model'])
-      self.fcgf_model = FCGFModel(num_feats, network_config['model_n_out'],
-                                  bn_momentum=network_config['bn_momentum'],
-                                  conv1_kernel_size=network_config['conv1_kernel_size'],
-                                  normalize_feature=network_config['normalize_feature'])
-    self.fcgf_model.load_state_dict(state['state_dict'])
-    self.fcgf_model = self.fcgf_model.to(self.device).eval()
-
-    num_feats = 6 if network_config.inlier_feature_type == 'coords' else 1
-    InlierModel = load_model(network_config['inlier_model'])
-    self.inlier_model = InlierModel(num_feats, 1, bn_momentum=network_config['bn_momentum'],
-                                    conv1_kernel_size=network_config['inlier_conv1_kernel_size'],
-                                    normalize_feature=False, D=6)
-    self.inlier_model.load_state_dict(state['state_dict_inlier'])
-    self.inlier_model = self.inlier_model.to(self.device).eval()
+    # FCGF extractor: current key names first, then the legacy ones of older checkpoints
+    # (reference :95-112); one dummy input channel (:96)
+    nc = network_config
+    legacy = 'feat_model' not in nc
+    self.fcgf_model = self._build_network(
+        nc['model' if legacy else 'feat_model'], state['state_dict'], in_channels=1,
+        out_channels=nc['model_n_out' if legacy else 'feat_model_n_out'],
+        conv1_kernel_size=nc['conv1_kernel_size' if legacy else 'feat_conv1_kernel_size'],
+        normalize_feature=nc['normalize_feature'], D=3)
+    # 6-D inlier network: 6 input channels only for the 'coords' feature type (:119)
+    self.inlier_model = self._build_network(
+        nc['inlier_model'], state['state_dict_inlier'],
+        in_channels=6 if nc.inlier_feature_type == 'coords' else 1, out_channels=1,
+        conv1_kernel_size=nc['inlier_conv1_kernel_size'], normalize_feature=False, D=6)
     self._pinned = {}
     self._log('=> loading finished')
+
+  def _build_network(self, name, weights, in_channels, out_channels, conv1_kernel_size, normalize_feature, D):
+    cls = load_model(name)
+    if cls is None:
+      raise KeyError(f'unknown model {name!r}')
+    net = cls(in_channels, out_channels, bn_momentum=self.network_config['bn_momentum'],
+              conv1_kernel_size=conv1_kernel_size, normalize_feature=normalize_feature, D=D)
+    net.load_state_dict(weights)
+    return net.to(self.device).eval()
 
   def _log(self, msg):
     if self.verbose:

@@ -352,13 +352,6 @@ __global__ void kernel_map_table_kernel(const int32_t* __restrict__ out_coords, 
   }
 }
 
-__global__ void kofs_kernel(const int32_t* __restrict__ block_ofs, int K, int bpk, int32_t* kofs,
-                            const dgr_keyspec_t* __restrict__ spec) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k <= K) kofs[k] = block_ofs[(int64_t)k * bpk];
-  if (k == K + 1) kofs[k] = spec != nullptr ? spec->overflow : 0;   // rides along with the host read
-}
-
 __global__ void kernel_map_fill_kernel(const int32_t* __restrict__ nbr, int64_t n_out,
                                        const int32_t* __restrict__ block_ofs,
                                        int32_t* __restrict__ in_idx, int32_t* __restrict__ out_idx) {

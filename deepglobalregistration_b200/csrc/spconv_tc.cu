@@ -32,7 +32,7 @@ using namespace tc;
 constexpr int kLoaderWarps = 8;
 constexpr int kLoaderThreads = kLoaderWarps * 32;   // warps 0..7: gather + TF32 split
 constexpr int kMmaWarp = kLoaderWarps;               // warp 8: tcgen05.mma issuer
-constexpr int kEpiWarp0 = kLoaderWarps + 1;          // warps 9..12: TMEM -> red.global
+// warps 9..12 (kLoaderWarps + 1 ..): epilogue, TMEM -> red.global
 constexpr int kThreadsTC = (kLoaderWarps + 5) * 32;  // 416
 constexpr int kTileM = 128;
 constexpr int kChunk = 32;               // floats of K per stage (128 bytes)

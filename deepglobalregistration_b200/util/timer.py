@@ -1,33 +1,67 @@
-"""Wall-clock stage timers with the reference's Timer/AverageMeter surface
-(util/timer.py:12-54): tic(), toc(average=True), .avg, .sum, .count - read by
-scripts/test_kitti.py:83,92-93 through DeepGlobalRegistration.feat_timer / reg_timer."""
+"""Stage timers exposing the attributes the reference's callers read from
+``DeepGlobalRegistration.feat_timer`` / ``reg_timer`` (scripts/test_kitti.py:83,92-93 use
+``tic()``, ``toc()``, ``.avg``; the reference class is util/timer.py:40-54).
+
+Host wall clock by default; ``Timer(sync=True)`` brackets the interval with a CUDA
+synchronisation so that it covers the GPU work enqueued in between (the reference's timers are
+only correct where an ``.item()`` happens to synchronise)."""
+import math
 import time
 
 
-class AverageMeter:
+class RunningStat:
+  """Count / mean / variance of a stream of samples (Welford), plus the last value."""
+
+  __slots__ = ('count', 'avg', '_m2', 'sum', 'val')
+
   def __init__(self):
     self.reset()
 
   def reset(self):
-    self.val = self.avg = 0.0
-    self.sum = self.sq_sum = 0.0
-    self.count = 0
-    self.var = 0.0
+    self.count, self.avg, self._m2, self.sum, self.val = 0, 0.0, 0.0, 0.0, 0.0
 
-  def update(self, val, n=1):
-    self.val = val
-    self.sum += val * n
-    self.sq_sum += val * val * n
-    self.count += n
-    self.avg = self.sum / self.count
-    self.var = self.sq_sum / self.count - self.avg ** 2
+  def update(self, value, n=1):
+    value = float(value)
+    for _ in range(int(n)):
+      self.count += 1
+      delta = value - self.avg
+      self.avg += delta / self.count
+      self._m2 += delta * (value - self.avg)
+    self.sum += value * n
+    self.val = value
+
+  @property
+  def var(self):
+    return self._m2 / self.count if self.count else 0.0
+
+  @property
+  def std(self):
+    return math.sqrt(self.var)
 
 
-class Timer(AverageMeter):
+class Timer(RunningStat):
+  __slots__ = ('sync', '_t0', 'diff')
+
+  def __init__(self, sync=False):
+    super().__init__()
+    self.sync, self._t0, self.diff = sync, None, 0.0
+
+  def _now(self):
+    if self.sync:
+      import torch
+      if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    return time.perf_counter()
+
   def tic(self):
-    self.start_time = time.time()
+    self._t0 = self._now()
 
   def toc(self, average=True):
-    self.diff = time.time() - self.start_time
+    if self._t0 is None:
+      raise RuntimeError('toc() without tic()')
+    self.diff = self._now() - self._t0
     self.update(self.diff)
     return self.avg if average else self.diff
+
+
+AverageMeter = RunningStat

@@ -56,3 +56,33 @@ def test_known_answer_rigid_copy():
   R, t = oreg.weighted_procrustes(X, X @ Rg.T + tg, np.ones((500, 1), np.float32))
   np.testing.assert_allclose(R.numpy(), Rg, atol=1e-6)
   np.testing.assert_allclose(t.numpy(), tg, atol=1e-6)
+
+
+def test_icp_oracle_known_answer():
+  """oracle/icp.py (open3d RegistrationICP restatement): a slightly perturbed rigid copy converges
+  back to the exact transform, with open3d's stop rule (both fitness and RMSE changes < 1e-6)."""
+  from deepglobalregistration_b200 import synthetic as syn
+  from oracle.icp import icp_point_to_point, kabsch
+  g = np.random.default_rng(0)
+  src = g.uniform(0, 2, size=(4000, 3))
+  T_gt = syn.random_se3(g, 30.0, 0.4)
+  tgt = syn.apply_se3(T_gt, src)
+  R, t = kabsch(src, tgt)
+  np.testing.assert_allclose(R, T_gt[:3, :3], atol=1e-10)
+  np.testing.assert_allclose(t, T_gt[:3, 3], atol=1e-10)
+  T_init = syn.random_se3(np.random.default_rng(1), 1.0, 0.01) @ T_gt
+  T, info = icp_point_to_point(src, tgt, 0.1, T_init)
+  te, re = syn.rte_rre(T, T_gt)
+  assert te < 1e-9 and re < 1e-7 and info['fitness'] == 1.0 and info['iterations'] <= 30
+  # no correspondence within the radius: the pose is left alone, fitness 0
+  T2, info2 = icp_point_to_point(src, tgt + 100.0, 0.1, np.eye(4))
+  assert np.array_equal(T2, np.eye(4)) and info2['fitness'] == 0.0
+
+
+def test_lidar_pair_is_one_scene_seen_from_two_poses():
+  from deepglobalregistration_b200 import synthetic as syn
+  from scipy.spatial import cKDTree
+  a, b, T = syn.lidar_pair(0)
+  assert 100_000 < len(a) < 130_000 and abs(len(a) - len(b)) < 5000 and not np.array_equal(a[:100], b[:100])
+  d, _ = cKDTree(b).query(syn.apply_se3(T, a[::50]))
+  assert np.median(d) < 0.3          # static structure lines up under the ground-truth motion
