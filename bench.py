@@ -326,11 +326,15 @@ def run_ours(args):
 
   t_start = time.time()
   thr0 = cgroup_throttled_ms()
+  ms0 = torch.cuda.memory_stats(dev)
   res = timed(args.steps, host_inputs=False, profile=True)     # `value`: scans resident in HBM
   t_mid = time.time()
   res_e2e = timed(args.steps, host_inputs=True)                 # `e2e`: host buffers in, pose out
   t_end = time.time()
   thr1 = cgroup_throttled_ms()
+  ms1 = torch.cuda.memory_stats(dev)
+  alloc_delta = {k: int(ms1.get(k, 0) - ms0.get(k, 0)) for k in ('num_device_alloc', 'num_device_free',
+                                                                  'num_alloc_retries', 'num_sync_all_streams')}
   clocks = sampler.stop(t_start, t_end) if sampler else None
 
   if rank != 0:
@@ -402,6 +406,7 @@ def run_ours(args):
           'kernel_share_of_step': kernel_share, 'cpu_baseline': cpu,
           'wall_ms_per_step': 1e3 * res['wall'] / K,
           'host_cgroup_throttled_ms_during_timing': (thr1 - thr0) if thr0 is not None and thr1 is not None else None,
+          'cuda_allocator_events_during_timing': alloc_delta,
           'host_threads': {'torch_intraop': torch.get_num_threads(), 'usable_cpus': effective_cpus()},
           'step_ms': {'min': min(res['steps_ms']), 'median': float(np.median(res['steps_ms'])),
                       'max': max(res['steps_ms']), 'all': [round(x, 2) for x in res['steps_ms']]},
