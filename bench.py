@@ -321,7 +321,6 @@ def run_ours(args):
   timed(args.steps, host_inputs=False)
   timed(args.steps, host_inputs=True)
   gc.collect()
-  gc.disable()
   log('[bench] warm-up done, timing')
 
   t_start = time.time()

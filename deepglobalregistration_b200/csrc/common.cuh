@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "dgr_b200.h"
 
 void dgr_set_error(const char* fmt, ...);
@@ -18,6 +20,18 @@ void dgr_note_launches(int n);   // bookkeeping for dgr_launch_count()
   } while (0)
 
 #define DGR_LAUNCH_CHECK() DGR_CUDA_CHECK(cudaGetLastError())
+
+// Opt a kernel in to `bytes` of dynamic shared memory - once per call site (and again only if a
+// later launch needs more), not before every launch: cudaFuncSetAttribute is a driver call that
+// takes the context lock.
+#define DGR_ENSURE_SMEM(func, bytes)                                                                 \
+  do {                                                                                               \
+    static std::atomic<int> cur_smem_{0};                                                            \
+    if ((int)(bytes) > cur_smem_.load(std::memory_order_relaxed)) {                                  \
+      DGR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      cur_smem_.store((int)(bytes), std::memory_order_relaxed);                                      \
+    }                                                                                                \
+  } while (0)
 
 #define DGR_ARG_CHECK(cond, msg)                                      \
   do {                                                                \

@@ -320,8 +320,8 @@ int32_t launch_knn_tc(const float* f0, int64_t n0, const float* f1, int64_t n1, 
                       cudaStream_t st) {
   constexpr int kChunks = C / 32;
   const size_t smem = sizeof(KnnShared) + 1024 + (size_t)kChunks * kATile + 2 * (size_t)kChunks * kBTile;
-  DGR_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DGR_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DGR_ENSURE_SMEM((knn_tc_kernel<C, 1>), smem);
+  DGR_ENSURE_SMEM((knn_tc_kernel<C, 2>), smem);
   const int row_tiles = (int)((n0 + kRowsA - 1) / kRowsA);
   const int col_tiles = (int)((n1 + kColsB - 1) / kColsB);
   int splits = (148 * 4 + row_tiles - 1) / row_tiles;

@@ -690,8 +690,7 @@ int32_t dgr_se3_register(const float* x, const float* y, const int32_t* idx1, co
   cudaStream_t st = (cudaStream_t)stream;
   pack_corr_kernel<<<dgr_blocks(n, 256), 256, 0, st>>>(x, y, idx1, w, n, pack_ws);
   const size_t smem = ((sizeof(RegShared) + 15) / 16) * 16 + (size_t)7 * kSmemPoints * sizeof(float);
-  DGR_CUDA_CHECK(cudaFuncSetAttribute(se3_register_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+  DGR_ENSURE_SMEM(se3_register_kernel, smem);
   const float eps = 1.1920928955078125e-07f;   // np.finfo(np.float32).eps, core/loss.py:44
   se3_register_kernel<<<kClusterSize, kRegThreads, smem, st>>>(pack_ws, n, quantization_size, max_iter,
                                                               max_break_count, break_threshold_ratio,

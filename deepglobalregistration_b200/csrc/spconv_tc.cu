@@ -605,8 +605,7 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
     int cols = 32;
     while (cols < n_acc * acc_cols + 64 * ns) cols <<= 1;
     const size_t smem_at = sizeof(TcAtShared) + 1024 + (size_t)ns * sb;
-    DGR_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_at_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem_at));
+    DGR_ENSURE_SMEM(spconv_tc_at_kernel, smem_at);
     spconv_tc_at_kernel<<<grid, kThreadsTC, smem_at, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
                                                            tile_k, tile_start, n_tiles, ns, cols, n_acc, acc_cols,
                                                            passes, out);
@@ -614,8 +613,7 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
     // CTA pairs on two tiles of the same offset, B tiles multicast to both (paired tile list)
     DGR_ARG_CHECK(n_tiles % 2 == 0, "a paired tile list has an even number of tiles");
     grid &= ~1;
-    DGR_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+    DGR_ENSURE_SMEM(spconv_tc_kernel<2>, smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreadsTC);
@@ -632,8 +630,7 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
                                       out_idx, kofs, tile_k, tile_start, (int)n_tiles, n_stages, tmem_cols,
                                       (int)passes, out));
   } else {
-    DGR_CUDA_CHECK(cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+    DGR_ENSURE_SMEM(spconv_tc_kernel<1>, smem);
     spconv_tc_kernel<1><<<grid, kThreadsTC, smem, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
                                                         tile_k, tile_start, n_tiles, n_stages, tmem_cols, passes,
                                                         out);

@@ -68,6 +68,11 @@ class CoordinateManager:
       if n_unique != coords.shape[0]:
         raise ValueError(f'{coords.shape[0] - n_unique} duplicate coordinates: the DGR hot path feeds '
                          'unique coordinates (sparse_quantize output) and relies on row order')
+    # NOTE: callers attach the manager to the very tensor they passed in (`coords._dgr_manager`);
+    # holding that same Python object here would close a reference cycle that only the garbage
+    # collector can free - hundreds of MB of CUDA memory per pair, a cudaMalloc storm in the caching
+    # allocator.  detach() gives an alias (same storage, new object, no back-reference).
+    coords = coords.detach()
     self.device = coords.device
     self.D = coords.shape[1] - 1
     self.spec = spec
