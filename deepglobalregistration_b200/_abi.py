@@ -63,6 +63,8 @@ SIGNATURES = {
     'dgr_inlier_coords': [_p, _p, _p, _i64, _p, _p],
     'dgr_sigmoid_clip_sum': [_p, _i64, _f32, _p, _p, _p],
     'dgr_icp_point_to_point': [_p, _i64, _p, _p, _p, _p, _i64, _i32, _f64, _f64, _p, _i32, _f64, _f64, _p, _p, _p],
+    'dgr_ransac_ws_elems': [_i64, _i64, _p],
+    'dgr_ransac_correspondence': [_p, _p, _p, _p, _i64, _f64, _i64, C.c_uint64, _p, _p, _p],
     'dgr_se3_register': [_p, _p, _p, _p, _i64, _f32, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p],
 }
 _RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_knn_tc_ws_elems': _i64, 'dgr_launch_count': _i64, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
@@ -546,4 +548,25 @@ def icp_point_to_point(src, tgt, tgt_manager, voxel, max_dist, T_init, max_iter=
   call('dgr_icp_point_to_point', ptr(src), src.shape[0], ptr(tgt), ptr(tgt_manager.spec), ptr(m.table.keys),
        ptr(m.table.vals), m.table.cap, int(batch), float(voxel), float(max_dist), ptr(T_init), int(max_iter),
        float(rel_fitness), float(rel_rmse), ptr(state), ptr(res), stream())
+  return res
+
+
+def ransac_correspondence(x, y, idx0, idx1, max_dist, num_hyp=4000000, seed=0):
+  """Safeguard RANSAC over the correspondences (x[idx0[i]], y[idx1[i]]) (an index of None means
+  arange).  x / y: CUDA float32 [n, 3]; idx: int32.  -> device double [20] (pose 16, fitness,
+  inlier RMSE, winning hypothesis, its inlier count)."""
+  _chk(x, torch.float32, 'x'); _chk(y, torch.float32, 'y')
+  dev = x.device
+  if idx0 is not None: _chk(idx0, torch.int32, 'idx0')
+  if idx1 is not None: _chk(idx1, torch.int32, 'idx1')
+  n = len(idx0) if idx0 is not None else (len(idx1) if idx1 is not None else x.shape[0])
+  if idx0 is not None and idx1 is not None and len(idx0) != len(idx1):
+    raise DgrError('idx0 and idx1 differ in length')
+  words = C.c_int64(0)
+  call('dgr_ransac_ws_elems', n, int(num_hyp), C.byref(words))
+  ws = scratch('ransac', words.value, torch.int64, dev)
+  res = torch.empty(20, dtype=torch.float64, device=dev)
+  call('dgr_ransac_correspondence', ptr(x), ptr(y), ptr(idx0) if idx0 is not None else None,
+       ptr(idx1) if idx1 is not None else None, n, float(max_dist), int(num_hyp), int(seed) & (2**64 - 1),
+       ptr(ws), ptr(res), stream())
   return res

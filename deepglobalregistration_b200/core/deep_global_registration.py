@@ -3,8 +3,9 @@
 
 Built path: voxelise -> FCGF features -> feature kNN -> 6-D inlier network -> weights ->
 weighted Procrustes + SE(3) refinement -> point-to-point ICP (``use_icp``, default True as
-in the reference).  The open3d RANSAC safeguard (:302-315) is a SURVEY.md §8f "next" row and
-is not built: that branch returns identity with ``last_branch`` set to 'safeguard'.
+in the reference).  When the weight sum is below the gate (:276-281) the pair goes to the
+safeguard branch (:302-315): RANSAC over the correspondences on the GPU
+(dgr_ransac_correspondence), followed by the same ICP.
 """
 import os
 
@@ -24,6 +25,10 @@ class DeepGlobalRegistration:
     self.clip_weight_thresh = self.config.clip_weight_thresh
     self.device = _abi.require_device(device)
     self.safeguard_method = 'correspondence'
+    # The reference calls RANSACConvergenceCriteria(4000000, num_iterations) (:62): 4 M hypotheses,
+    # and the 80000 it passes lands in open3d's confidence slot (clamped to 1 = no early exit).
+    self.safeguard_max_iteration = 4000000
+    self.safeguard_seed = 0       # open3d draws from std::random_device; here a call is reproducible
     self.use_icp = True           # as the reference; GPU point-to-point ICP (dgr_icp_point_to_point)
     self.verbose = getattr(config, 'verbose', True)
     self.feat_timer = Timer()
@@ -165,9 +170,33 @@ class DeepGlobalRegistration:
     sinput = SparseTensor(inlier_feats, coordinates=coords, device=self.device)
     return self.inlier_model.forward_fused(sinput).F
 
-  def safeguard_registration(self, *args, **kwargs):
-    raise NotImplementedError('the RANSAC safeguard (open3d, core/deep_global_registration.py:50-64) '
-                              'is a "next" row of the build plan and is not built')
+  def safeguard_registration(self, pcd0, pcd1, idx0, idx1, feats0, feats1, distance_threshold,
+                             num_iterations):
+    """Reference :219-236.  pcd0 / pcd1: [N, 3] points (CUDA float32 tensors, or anything
+    np.asarray takes); idx0 / idx1: correspondence indices (idx0 None = arange).  As in the
+    reference, ``num_iterations`` does not bound the search (it lands in open3d's confidence
+    slot, :62); ``self.safeguard_max_iteration`` hypotheses are evaluated.  -> 4x4 float64."""
+    if self.safeguard_method == 'fcgf_feature_matching':
+      raise NotImplementedError("safeguard_method 'fcgf_feature_matching' (open3d feature-matching RANSAC, "
+                                'core/deep_global_registration.py:27-46) is not built; the default '
+                                "'correspondence' is")
+    if self.safeguard_method != 'correspondence':
+      raise ValueError('Undefined')
+    res = self._safeguard_launch(pcd0, pcd1, idx0, idx1, distance_threshold)
+    self.last_safeguard = res = res.cpu().numpy()
+    return res[:16].reshape(4, 4).copy()
+
+  def _safeguard_launch(self, pcd0, pcd1, idx0, idx1, distance_threshold):
+    def points(p):
+      if not isinstance(p, torch.Tensor):
+        p = torch.from_numpy(np.ascontiguousarray(np.asarray(getattr(p, 'points', p)), dtype=np.float32))
+      return p.to(self.device, torch.float32).contiguous()
+
+    def index(i):
+      return None if i is None else torch.as_tensor(i).to(self.device, torch.int32).contiguous()
+
+    return _abi.ransac_correspondence(points(pcd0), points(pcd1), index(idx0), index(idx1), distance_threshold,
+                                      num_hyp=self.safeguard_max_iteration, seed=self.safeguard_seed)
 
   # ---------------------------------------------------------------------------------------
   def register(self, xyz0, xyz1, inlier_thr=0.00):
@@ -224,13 +253,24 @@ class DeepGlobalRegistration:
                             n_active=int(res[15]))
       dgr_time = self.reg_timer.toc()
       self._log(f'=> DGR takes {dgr_time:.2} s')
+      icp = host[17:37] if self.use_icp else None
     else:
+      # > Case 1: Safeguard RANSAC + (optional) ICP (reference :302-315), one more host read
       self.last_branch = 'safeguard'
-      self.reg_timer.toc()
-      self._log('=> weight sum below threshold: the reference falls back to open3d RANSAC here; the '
-                'safeguard is not built, returning identity')
-    if self.use_icp and self.last_branch == 'procrustes':
-      icp = host[17:37]
+      with torch.no_grad():
+        ransac_dev = self._safeguard_launch(xyz0, xyz1, None, idx1, 2 * self.voxel_size)
+        parts = [ransac_dev]
+        if self.use_icp:
+          parts.append(_abi.icp_point_to_point(xyz0, xyz1, coords1._dgr_manager, self.voxel_size,
+                                               2 * self.voxel_size, ransac_dev[:12].contiguous(), batch=1))
+        host = torch.cat(parts).cpu().numpy()
+      T = host[:16].reshape(4, 4).copy()
+      self.last_info.update(ransac_fitness=float(host[16]), ransac_inlier_rmse=float(host[17]),
+                            ransac_hypothesis=int(host[18]), ransac_inliers=int(host[19]))
+      icp = host[20:40] if self.use_icp else None
+      safeguard_time = self.reg_timer.toc()
+      self._log(f'=> Safeguard takes {safeguard_time:.2} s')
+    if icp is not None:
       T = icp[:16].reshape(4, 4).copy()
       self.last_info.update(icp_fitness=float(icp[16]), icp_inlier_rmse=float(icp[17]),
                             icp_iterations=int(icp[18]))

@@ -260,3 +260,20 @@ def make_checkpoint(seed=0, voxel_size=0.05, feat_conv1_kernel_size=7, feat_mode
     state['state_dict_inlier'] = resunet_state_dict(seed + 1, nin, 1, inlier_conv1_kernel_size, 6,
                                                     channels, tr_channels)
   return state
+
+
+def correspondence_set(seed, n=1500, inlier_frac=0.3, noise=0.004):
+  """Putative correspondences for the safeguard (RANSAC) tests: source points in a 3 m cube, a
+  random pose (<= 40 deg, <= 0.5 m), `inlier_frac` of the targets = pose(source) + N(0, noise),
+  the rest uniform clutter; target rows shuffled so idx1 is a real gather.
+  -> (src f32 [n,3], tgt f32 [n,3], idx0, idx1, T_gt, inlier mask)."""
+  g = np.random.default_rng(seed)
+  P = g.uniform(-1.5, 1.5, size=(n, 3)).astype(np.float32)
+  T = random_se3(g, 40.0, 0.5)
+  Q = apply_se3(T, P.astype(np.float64)) + g.normal(0, noise, size=(n, 3))
+  out = g.random(n) >= inlier_frac
+  Q[out] = g.uniform(-2.0, 2.0, size=(int(out.sum()), 3))
+  perm = g.permutation(n)
+  tgt = np.empty_like(Q)
+  tgt[perm] = Q
+  return P, tgt.astype(np.float32), np.arange(n), perm, T, ~out

@@ -244,6 +244,22 @@ int32_t dgr_icp_point_to_point(const float* src, int64_t n_src, const float* tgt
                                double rel_fitness, double rel_rmse, double* state_ws, double* result,
                                void* stream);
 
+/* ---- Safeguard RANSAC: open3d registration_ransac_based_on_correspondence as
+ *      called at core/deep_global_registration.py:50-64 (from :302-315) ---------------------- */
+/* Correspondence i pairs x[idx0[i]] with y[idx1[i]] (a null index array means i itself).
+ * num_hyp hypotheses of 4 correspondences each (Umeyama without scaling, fp64), every one scored
+ * on ALL correspondences: more inliers (|R p + t - q| < max_dist) wins, then the lower inlier
+ * RMSE, then the lower hypothesis number; no early exit (the reference's criteria put 80000 in
+ * the confidence slot, which open3d clamps to 1).  Sampling is a counter hash of (seed,
+ * hypothesis, slot), so a call is reproducible.
+ * ws: dgr_ransac_ws_elems() 8-byte words; result: device double[20] = 4x4 pose (identity when no
+ * hypothesis has an inlier), fitness, inlier RMSE (both re-evaluated in fp64), winning hypothesis
+ * (-1 if none), its inlier count. */
+int32_t dgr_ransac_ws_elems(int64_t n_corr, int64_t num_hyp, int64_t* n_elems);
+int32_t dgr_ransac_correspondence(const float* x, const float* y, const int32_t* idx0, const int32_t* idx1,
+                                  int64_t n_corr, double max_dist, int64_t num_hyp, uint64_t seed,
+                                  uint64_t* ws, double* result, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

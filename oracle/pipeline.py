@@ -1,8 +1,8 @@
 """ORACLE (test infrastructure only) - the whole pairwise-registration hot path on
 the CPU, stage by stage, following DeepGlobalRegistration.register()
-(core/deep_global_registration.py:238-324) up to and including the SE(3)
-refinement; the open3d ICP / RANSAC steps (:302-322) are outside the built path
-and excluded on both sides.
+(core/deep_global_registration.py:238-324): Procrustes + SE(3) refinement, or
+the RANSAC safeguard (:302-315, oracle/ransac.py) when the weight sum is below
+the gate, then optionally the ICP fine-tune (:317-322, oracle/icp.py).
 
 Each stage returns its tensors so that GPU parity tests can tap in anywhere and
 feed the oracle's outputs of stage k into the CUDA stage k+1 (stage-isolated
@@ -50,10 +50,11 @@ def inlier_logits(state, coords6, feats):
                          False)
 
 
-def register(state, xyz0, xyz1, clip_weight_thresh=0.05, use_icp=False):
-  """Returns (T 4x4 float64, taps dict).  T is identity when the weight-sum gate
-  (:276-281) sends the pair to the safeguard branch, which is not part of the
-  built path; taps['branch'] says which branch was taken."""
+def register(state, xyz0, xyz1, clip_weight_thresh=0.05, use_icp=False, safeguard_max_iteration=0,
+             safeguard_seed=0):
+  """Returns (T 4x4 float64, taps dict); taps['branch'] says which branch the weight-sum gate
+  (:276-281) took.  The safeguard branch runs safeguard_max_iteration RANSAC hypotheses (the
+  reference: 4 M; 0 = skip and return identity, for tests that only look at the gate)."""
   cfg = state['config']
   vs = cfg['voxel_size']
   p0, c0, sel0 = preprocess(xyz0, vs)
@@ -72,10 +73,15 @@ def register(state, xyz0, xyz1, clip_weight_thresh=0.05, use_icp=False):
     T[:3, :3] = R.numpy()
     T[:3, 3] = t.numpy().reshape(3)
     taps.update(branch='procrustes', refine=info, T_refined=T.copy())
-    if use_icp:      # :317-322
-      from .icp import icp_point_to_point
-      T, icp_info = icp_point_to_point(p0, p1, 2 * vs, T)
-      taps.update(icp=icp_info)
   else:
     taps.update(branch='safeguard')
+    if safeguard_max_iteration > 0:      # :302-315
+      from .ransac import ransac_correspondence
+      T, info = ransac_correspondence(p0, p1, np.arange(len(idx1)), idx1, 2 * vs, safeguard_max_iteration,
+                                      safeguard_seed)
+      taps.update(ransac=info, T_ransac=T.copy())
+  if use_icp and (taps['branch'] == 'procrustes' or safeguard_max_iteration > 0):      # :317-322
+    from .icp import icp_point_to_point
+    T, icp_info = icp_point_to_point(p0, p1, 2 * vs, T)
+    taps.update(icp=icp_info)
   return T, taps

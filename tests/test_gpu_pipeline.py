@@ -165,15 +165,22 @@ def test_checkpoint_file_boundary(tmp_path, state):
 @pytest.mark.parametrize('n_raw', [1, 3, 40, 300])
 def test_register_tiny_clouds(dgr, state, n_raw):
   """Degenerate sizes: single voxels, fewer voxels than one 128-row tile, empty coarse
-  neighbourhoods.  The weight-sum gate (>= 200) sends these to the safeguard branch, which
-  must be reported, not crash; every stage before it must still agree with the oracle."""
+  neighbourhoods.  The weight-sum gate (>= 200) sends these to the safeguard branch (RANSAC on
+  a handful of correspondences, mostly degenerate draws), which must return a rigid pose, not
+  crash; every stage before it must still agree with the oracle."""
   g = np.random.default_rng(n_raw)
   xyz0 = g.uniform(0, 0.6, size=(n_raw, 3))
   xyz1 = xyz0 + 0.05
-  T = dgr.register(xyz0, xyz1)
+  dgr.safeguard_max_iteration = 20000
+  try:
+    T = dgr.register(xyz0, xyz1)
+  finally:
+    dgr.safeguard_max_iteration = 4000000
   T_o, taps = op.register(state, xyz0, xyz1)
   assert dgr.last_branch == taps['branch'] == 'safeguard'
-  assert np.array_equal(T, np.eye(4))
+  R = T[:3, :3]
+  assert np.allclose(R @ R.T, np.eye(3), atol=1e-9) and abs(np.linalg.det(R) - 1) < 1e-9
+  assert np.array_equal(T[3], [0, 0, 0, 1]) and dgr.last_info['ransac_inliers'] >= 1
   assert dgr.last_info['n0'] == len(taps['coords0'])
   assert abs(dgr.last_info['wsum'] - taps['wsum']) <= 1e-3 * max(1.0, taps['wsum'])
 
@@ -184,8 +191,52 @@ def test_preprocess_rejects_unknown_input(dgr):
 
 
 def test_unbuilt_stages_fail_loudly(dgr):
-  with pytest.raises(NotImplementedError):
-    dgr.safeguard_registration()
+  dgr.safeguard_method = 'fcgf_feature_matching'
+  try:
+    with pytest.raises(NotImplementedError):
+      dgr.safeguard_registration(None, None, None, None, None, None, 0.1, 80000)
+  finally:
+    dgr.safeguard_method = 'correspondence'
+
+
+def test_safeguard_branch_known_answer():
+  """Force the weight-sum gate shut (clip threshold 1 zeroes every weight) on the rigid-copy
+  pair: the safeguard's RANSAC over the (exact) correspondences, then ICP, must recover the
+  shift; the oracle's safeguard on the same hypotheses agrees."""
+  from deepglobalregistration_b200 import me as ME
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+  from deepglobalregistration_b200.util.calibrate import calibrate_batchnorm
+  vs = 0.0625
+  st = syn.make_checkpoint(4, voxel_size=vs)
+  d = DeepGlobalRegistration(types.SimpleNamespace(weights=st, clip_weight_thresh=1.0, verbose=False))
+  xyz0 = syn.room_scan(2, 20000, EXTENT, scene_seed=1)
+  T_gt = np.eye(4)
+  T_gt[:3, 3] = vs * np.array([8, -16, 24])
+  xyz1 = syn.apply_se3(T_gt, xyz0)
+  with torch.no_grad():
+    _, c0, f0 = d.preprocess(xyz0)
+    calibrate_batchnorm(d.fcgf_model, ME.SparseTensor(f0, coordinates=c0, device='cuda'))
+  st['state_dict'] = {k: v.detach().cpu().clone() for k, v in d.fcgf_model.state_dict().items()}
+  d.safeguard_max_iteration, d.safeguard_seed = 3000, 11
+  for use_icp in (False, True):
+    d.use_icp = use_icp
+    T = d.register(xyz0, xyz1)
+    assert d.last_branch == 'safeguard' and d.last_info['wsum'] == 0.0
+    te, re = syn.rte_rre(T, T_gt)
+    assert te <= 1e-3 and re <= 1e-3, (use_icp, te, re, d.last_info)
+    assert d.last_info['ransac_fitness'] > 0.99
+  T_o, taps = op.register(st, xyz0, xyz1, clip_weight_thresh=1.0, use_icp=True, safeguard_max_iteration=3000,
+                          safeguard_seed=11)
+  assert taps['branch'] == 'safeguard'
+  te, re = syn.rte_rre(T, T_o)
+  assert te <= 1e-3 and re <= 1e-3, (te, re, taps['ransac'], taps.get('icp'))
+  # the public method, called the way the reference calls it (:302-311)
+  with torch.no_grad():
+    p0, _, _ = d.preprocess(xyz0, 0, _batch=0)
+    p1, _, _ = d.preprocess(xyz1, 1, _batch=1)
+  T_s = d.safeguard_registration(p0, p1, np.arange(len(taps['idx1'])), taps['idx1'], None, None, 2 * vs,
+                                 num_iterations=80000)
+  np.testing.assert_allclose(T_s, taps['T_ransac'], atol=1e-6)
 
 
 def test_icp_kernel_vs_oracle():
