@@ -52,15 +52,26 @@ def gather_results(local_rows, n_pairs, device=None):
   return out
 
 
+def _cloud(item):
+  """A pair member is an array / tensor / point-cloud object, or the path of a file to read when
+  its turn comes (so a rank only ever loads its own share)."""
+  if isinstance(item, (str, bytes)) or hasattr(item, '__fspath__'):
+    from . import io as dio
+    return dio.read_points(str(item) if not isinstance(item, bytes) else item.decode())
+  return item
+
+
 def register_pairs(dgr, pairs, device=None):
-  """Register this rank's share of `pairs` ([(xyz0, xyz1), ...]) with `dgr` and gather all
-  results.  Returns [len(pairs), 20] float32, identical on every rank."""
+  """Register this rank's share of `pairs` ([(xyz0, xyz1), ...]; members may be file paths) with
+  `dgr` and gather all results.  Returns [len(pairs), 20] float32, identical on every rank.  The
+  milliseconds column times register() only, not the file reads."""
   world = dist.get_world_size() if dist.is_initialized() else 1
   rank = dist.get_rank() if dist.is_initialized() else 0
   rows = []
   for i in shard_indices(len(pairs), rank, world):
+    xyz0, xyz1 = _cloud(pairs[i][0]), _cloud(pairs[i][1])
     t = time.perf_counter()
-    T = dgr.register(pairs[i][0], pairs[i][1])
+    T = dgr.register(xyz0, xyz1)
     info = getattr(dgr, 'last_info', {})
     rows.append(pack_result(T, info.get('wsum', 0.0), info.get('iterations', 0),
                             getattr(dgr, 'last_branch', None), 1e3 * (time.perf_counter() - t)))
