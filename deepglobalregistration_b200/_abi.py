@@ -402,6 +402,7 @@ def pack_weight_tf32(weight, K, cin, cout):
 # tiles.  All three are parity-tested; all three run at the same speed on the wide layers, which
 # is how the L2->SM ingress bound was identified.
 TC_VARIANT = int(os.environ.get('DGR_TC_VARIANT', '1'))
+TC_PAIR_MIN_COUT = int(os.environ.get('DGR_TC_PAIR_MIN_COUT', '128'))
 
 # When set to a list, every sparse-convolution launch appends
 # (kernel name, start event, end event, algorithmic flops, gather-scatter-model bytes):
@@ -432,7 +433,9 @@ def spconv_tc_fwd(feat, weight_t, km, out, passes=3, cluster=None):
   assert feat.shape[0] == km.n_in and out.shape[0] == km.n_out
   if cluster is None:
     cluster = TC_VARIANT
-  if cluster == 2:
+    if cluster == 3 and cout < TC_PAIR_MIN_COUT:
+      cluster = 1               # narrow layers are bound by the gather, not by weight ingress: no pairing
+  if cluster in (2, 3):
     tk, ts, nt = km.paired_tiles()
   else:
     tk, ts, nt = km.tile_k, km.tile_start, km.n_tiles

@@ -22,6 +22,8 @@
 // cached per layer by the host): per (offset, 32-channel chunk) one contiguous slab holding the
 // TF32 hi tile and the lo tile in shared-memory image order, streamed by a single
 // cp.async.bulk (TMA engine) per stage - the loader threads only touch the gathered rows.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -87,6 +89,43 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+
+// Epilogue scatter of 32 accumulator columns [col, col + 32) of a warp's 32 rows.
+// tcgen05.ld hands every thread ONE row (lane = row): scattering from that layout makes each warp
+// instruction touch 32 different output rows with 16 bytes each - 32 memory requests per
+// instruction, 8192 per tile at cout = 256, which is what bounded the wide layers (every other
+// knob - atomics vs stores, weight multicast, A in tensor memory, cta_group::2, gather lookahead -
+// left their time unchanged).  Transposing through a 4 KB shared-memory tile (XOR-swizzled, no
+// bank conflicts) lets 8 lanes cover one row's 128-byte line: 4 full lines per instruction.
+__device__ __forceinline__ void scatter32_lines(unsigned char* stg, int lane, float* __restrict__ out, int cout,
+                                                int col, int j, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+        make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+  const int p = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int R = rsub + 4 * k;
+    const int jr = __shfl_sync(0xffffffffu, j, R);
+    const float4 x = *reinterpret_cast<const float4*>(stg + R * 128 + ((p ^ (R & 7)) << 4));
+    if (jr >= 0) red_add_v4(out + (size_t)jr * cout + col + p * 4, x.x, x.y, x.z, x.w);
+  }
+  __syncwarp();      // the tile is rewritten by the next column group
+}
+__device__ __forceinline__ void scatter32_rows(float* __restrict__ out, int cout, int col, int j,
+                                               const uint32_t (&v)[32]) {
+  if (j >= 0) {
+    float* dst = out + (size_t)j * cout + col;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+  }
+}
+constexpr int kEpiStageBytes = 4 * 4096;     // one 32 x 32 fp32 transpose tile per epilogue warp
+
 struct TcShared {
   unsigned long long full[4];      // gathered A tiles (256 arrivals) + B hi tile (bulk-copy bytes)
   unsigned long long full_lo[4];   // B lo tile (bulk-copy bytes): needed only by the third product
@@ -100,13 +139,13 @@ struct TcShared {
 // (tile = blockIdx.x + i * gridDim.x) and meet only through mbarriers:
 //   loaders  --full[s]-->  MMA issuer  --empty[s]-->  loaders        (shared-memory stages)
 //   MMA issuer  --acc_full[b]-->  epilogue  --acc_empty[b]-->  MMA   (two TMEM accumulators)
-template <int kCluster>
+template <int kCluster, int kPD>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __restrict__ wt, int cout,
                  const int32_t* __restrict__ in_idx, const int32_t* __restrict__ out_idx,
                  const int32_t* __restrict__ kofs, const int32_t* __restrict__ tile_k,
                  const int32_t* __restrict__ tile_start, int n_tiles, int n_stages, int tmem_cols,
-                 int passes, float* __restrict__ out) {
+                 int passes, int epi, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   TcShared& sh = *reinterpret_cast<TcShared*>(smem_dyn);
   // stage buffers start at the next 1024-byte boundary (SWIZZLE_128B atom alignment)
@@ -170,23 +209,35 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
                                                                     piece * 4))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    // The gather runs kPD chunks ahead of the chunk being stored (register queue q[0..kPD]): a
+    // stage can only be published when the SLOWEST of its 1024 row loads has landed, and with ~1/5
+    // of the rows missing L2 that is a loaded-DRAM latency (~3k cycles) every chunk - more than one
+    // chunk's worth of MMAs, so one chunk of lookahead left the tensor pipe waiting.
     uint32_t it = 0;
-    int src[4], nsrc[4];
-    float4 a_cur[4], a_nxt[4];
-    load_rows(blockIdx.x, src);
-    load_a(src, 0, a_cur);
+    float4 q[kPD + 1][4];
+    int pf_tile = blockIdx.x, pf_c = 0;          // prefetch cursor (tile, chunk) and the rows of its tile
+    int pf_src[4], pf_nsrc[4];                   // ... and of the tile after it (indices one tile ahead)
+    load_rows(pf_tile, pf_src);
+    if (pf_tile + (int)gridDim.x < n_tiles) load_rows(pf_tile + gridDim.x, pf_nsrc);
+    auto pf_issue = [&](float4 (&v)[4]) {
+      if (pf_tile < n_tiles) load_a(pf_src, pf_c, v);
+      if (++pf_c == n_chunks) {
+        pf_c = 0;
+        pf_tile += gridDim.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pf_src[i] = pf_nsrc[i];
+        if (pf_tile + (int)gridDim.x < n_tiles) load_rows(pf_tile + gridDim.x, pf_nsrc);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < kPD; ++d) pf_issue(q[d]);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int kappa = tile_k[tile];
-      const int next_tile = tile + gridDim.x;
-      const bool has_next = next_tile < n_tiles;
-      if (has_next) load_rows(next_tile, nsrc);
       const float* slab = wt + (size_t)kappa * n_chunks * (slab_bytes / 4);
       for (int c = 0; c < n_chunks; ++c, ++it) {
         const int s = it % n_stages;
         const uint32_t ph = (it / n_stages) & 1;
-        // prefetch the next chunk's rows (same tile, or chunk 0 of this CTA's next tile)
-        if (c + 1 < n_chunks) load_a(src, c + 1, a_nxt);
-        else if (has_next) load_a(nsrc, 0, a_nxt);
+        pf_issue(q[kPD]);
         mbar_wait(smem_u32(&sh.empty[s]), ph ^ 1);
         unsigned char* a_hi = stage0 + (size_t)s * stage_bytes;
         unsigned char* a_lo = a_hi + kATileBytes;
@@ -211,14 +262,14 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_store(a_cur[i], a_hi, a_lo, a_off + i * 4096);
+        for (int i = 0; i < 4; ++i) split_store(q[0][i], a_hi, a_lo, a_off + i * 4096);
         fence_proxy_async();
         mbar_arrive(smem_u32(&sh.full[s]));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a_cur[i] = a_nxt[i];
-      }
+        for (int d = 0; d < kPD; ++d)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) src[i] = nsrc[i];
+          for (int i = 0; i < 4; ++i) q[d][i] = q[d + 1][i];
+      }
     }
   } else if (warp == kMmaWarp) {
     // ================================ MMA issuer =========================================
@@ -268,6 +319,7 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
   } else {
     // ================================ epilogue ===========================================
     const int lane_grp = warp & 3;            // TMEM lanes 32 * (warp % 4) .. + 31
+    unsigned char* epi_stage = stage0 + (size_t)n_stages * stage_bytes + (warp - kLoaderWarps - 1) * 4096;
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
       const uint32_t buf = tile_iter & 1;
@@ -283,13 +335,8 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
       for (; col + 32 <= cout; col += 32) {
         uint32_t v[32];
         tc_ld32(taddr + col, v);
-        if (j >= 0) {
-          float* dst = out + (size_t)j * cout + col;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-        }
+        if (epi) scatter32_lines(epi_stage, lane, out, cout, col, j, v);
+        else scatter32_rows(out, cout, col, j, v);
       }
       if (col < cout) {   // cout % 32 == 16
         uint32_t v[16];
@@ -522,6 +569,284 @@ spconv_tc_at_kernel(const float* __restrict__ in_feat, int cin, const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// CTA-PAIR variant (tcgen05 cta_group::2): two CTAs of a cluster (the two SMs of a TPC) work on
+// two 128-pair tiles of the SAME kernel offset as ONE M = 256 MMA.  Each CTA gathers its own
+// 128 rows of A and holds only HALF of every weight tile (B rows = output channels
+// [rank * cout/2, (rank + 1) * cout/2)); the tensor core reads the peer's half over the pair's
+// on-chip path.  What every SM must RECEIVE per 32-channel chunk drops from 64 KB + 16 KB to
+// 32 KB + 16 KB - the wide layers are bound by exactly that ingress.
+//
+// Protocol (rank 0 = leader issues all MMAs):
+//   full[s]       local: 256 loader arrivals + this CTA's two B halves (bulk-copy bytes)
+//   peer_full[s]  leader's: the peer's relay thread arrives once ITS full[s] has completed
+//   empty[s]      both:  tcgen05.commit.cta_group::2 multicast - the stage may be refilled
+//   acc_full[b]   both:  multicast commit - the accumulator (128 lanes x cout in each CTA) is final
+//   acc_empty[b]  leader's: 128 local + 128 remote epilogue threads have drained accumulator b
+// ---------------------------------------------------------------------------------------
+struct Tc2Shared {
+  unsigned long long full[4];
+  unsigned long long peer_full[4];
+  unsigned long long empty[4];
+  unsigned long long acc_full[2];
+  unsigned long long acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)0x3)
+      : "memory");
+}
+
+template <int kPD>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* __restrict__ wt, int cout,
+                      const int32_t* __restrict__ in_idx, const int32_t* __restrict__ out_idx,
+                      const int32_t* __restrict__ kofs, const int32_t* __restrict__ tile_k,
+                      const int32_t* __restrict__ tile_start, int n_tiles, int n_stages, int tmem_cols,
+                      int passes, int epi, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  Tc2Shared& sh = *reinterpret_cast<Tc2Shared*>(smem_dyn);
+  unsigned char* stage0 = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + sizeof(Tc2Shared) + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = cout * 128;             // a whole B tile (hi or lo) in the packed slab
+  const int b_half_bytes = b_tile_bytes >> 1;      // what this CTA holds of it
+  const int stage_bytes = 2 * kATileBytes + 2 * b_half_bytes;
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int n_chunks = cin / kChunk;
+  const uint32_t acc_stride = (uint32_t)tmem_cols >> 1;
+  const uint32_t rank = cluster_ctarank();
+  const int n_pairs = n_tiles >> 1;
+  const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+
+  if (t == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(smem_u32(&sh.full[s]), kLoaderThreads);
+      mbar_init(smem_u32(&sh.peer_full[s]), 1);
+      mbar_init(smem_u32(&sh.empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&sh.acc_full[b]), 1);
+      mbar_init(smem_u32(&sh.acc_empty[b]), 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {      // pair-wide allocation: the same warp of BOTH CTAs issues it
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&sh.tmem_base)),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before anyone signals across
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_base;
+
+  if (warp < kLoaderWarps) {
+    // ================================ loaders (both CTAs) ================================
+    const int piece = t & 7, rgrp = t >> 3;
+    const uint32_t a_off = (uint32_t)(rgrp * 128 + ((piece ^ (rgrp & 7)) << 4));
+    const uint32_t slab_floats = 2u * (uint32_t)b_tile_bytes / 4;
+    auto load_rows = [&](int tile_id, int (&src)[4]) {
+      const int kap = tile_k[tile_id];
+      const int q0 = tile_start[tile_id];
+      const int nrows = min(kTileM, kofs[kap + 1] - q0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 32 + rgrp;
+        src[i] = (r < nrows) ? __ldg(in_idx + q0 + r) : -1;
+      }
+    };
+    auto load_a = [&](const int (&src)[4], int c, float4 (&v)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        v[i] = src[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)src[i] * cin + c * kChunk +
+                                                                    piece * 4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    uint32_t it = 0;
+    const int tstep = 2 * pair_step;             // this CTA's tiles: 2 * pair + rank
+    float4 q[kPD + 1][4];                        // gather queue, kPD chunks ahead (see spconv_tc_kernel)
+    int pf_tile = 2 * pair0 + (int)rank, pf_c = 0;
+    int pf_src[4], pf_nsrc[4];
+    if (pf_tile < n_tiles) load_rows(pf_tile, pf_src);
+    if (pf_tile + tstep < n_tiles) load_rows(pf_tile + tstep, pf_nsrc);
+    auto pf_issue = [&](float4 (&v)[4]) {
+      if (pf_tile < n_tiles) load_a(pf_src, pf_c, v);
+      if (++pf_c == n_chunks) {
+        pf_c = 0;
+        pf_tile += tstep;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pf_src[i] = pf_nsrc[i];
+        if (pf_tile + tstep < n_tiles) load_rows(pf_tile + tstep, pf_nsrc);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < kPD; ++d) pf_issue(q[d]);
+    for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+      const int tile = 2 * pair + (int)rank;
+      const int kappa = tile_k[tile];
+      const float* slab = wt + (size_t)kappa * n_chunks * slab_floats;
+      for (int c = 0; c < n_chunks; ++c, ++it) {
+        const int s = it % n_stages;
+        const uint32_t ph = (it / n_stages) & 1;
+        pf_issue(q[kPD]);
+        mbar_wait(smem_u32(&sh.empty[s]), ph ^ 1);
+        unsigned char* a_hi = stage0 + (size_t)s * stage_bytes;
+        unsigned char* a_lo = a_hi + kATileBytes;
+        if (t == 0) {
+          // this CTA's half (rows rank * cout/2 ..) of the hi tile and of the lo tile
+          const float* bsrc = slab + (size_t)c * slab_floats + (size_t)rank * (b_half_bytes / 4);
+          mbar_expect_tx(smem_u32(&sh.full[s]), 2u * (uint32_t)b_half_bytes);
+          bulk_g2s(smem_u32(a_lo + kATileBytes), bsrc, (uint32_t)b_half_bytes, smem_u32(&sh.full[s]));
+          bulk_g2s(smem_u32(a_lo + kATileBytes + b_half_bytes), bsrc + b_tile_bytes / 4, (uint32_t)b_half_bytes,
+                   smem_u32(&sh.full[s]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_store(q[0][i], a_hi, a_lo, a_off + i * 4096);
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&sh.full[s]));
+#pragma unroll
+        for (int d = 0; d < kPD; ++d)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) q[d][i] = q[d + 1][i];
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (rank != 0) {
+      // ============================ peer: relay "my stage is full" to the leader ==========
+      uint32_t it = 0;
+      for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+          const int s = it % n_stages;
+          const uint32_t ph = (it / n_stages) & 1;
+          mbar_wait(smem_u32(&sh.full[s]), ph);
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sh.peer_full[s]), 0));
+          __syncwarp();
+        }
+      }
+    } else {
+      // ============================ leader: MMA issuer for the pair =======================
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = cout, M = 256 (128 per CTA)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cout >> 3) << 17) |
+                             ((uint32_t)((2 * kTileM) >> 4) << 24);
+      uint32_t it = 0, tile_iter = 0;
+      for (int pair = pair0; pair < n_pairs; pair += pair_step, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1;
+        const uint32_t tmem_d = tmem_base + buf * acc_stride;
+        mbar_wait_cluster(smem_u32(&sh.acc_empty[buf]), ((tile_iter >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+          const int s = it % n_stages;
+          const uint32_t ph = (it / n_stages) & 1;
+          mbar_wait(smem_u32(&sh.full[s]), ph);
+          mbar_wait_cluster(smem_u32(&sh.peer_full[s]), ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_bytes);
+            const uint32_t a_lo = a_hi + kATileBytes;
+            const uint32_t b_hi = a_lo + kATileBytes;
+            const uint32_t b_lo = b_hi + b_half_bytes;
+#pragma unroll
+            for (int ks = 0; ks < kChunk / 8; ++ks) {
+              const uint32_t ko = ks * 32;
+              const uint64_t dbh = umma_desc(b_hi + ko);
+              tc_mma_tf32_pair(tmem_d, umma_desc(a_hi + ko), dbh, idesc, (c | ks) != 0);
+              if (passes == 3) {
+                tc_mma_tf32_pair(tmem_d, umma_desc(a_lo + ko), dbh, idesc, 1);
+                tc_mma_tf32_pair(tmem_d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1);
+              }
+            }
+            tc_commit_pair(smem_u32(&sh.empty[s]));                       // frees the stage in both CTAs
+            if (c == n_chunks - 1) tc_commit_pair(smem_u32(&sh.acc_full[buf]));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (both CTAs, own 128 rows) ==================
+    const int lane_grp = warp & 3;
+    unsigned char* epi_stage = stage0 + (size_t)n_stages * stage_bytes + (warp - kLoaderWarps - 1) * 4096;
+    uint32_t tile_iter = 0;
+    for (int pair = pair0; pair < n_pairs; pair += pair_step, ++tile_iter) {
+      const int tile = 2 * pair + (int)rank;
+      const uint32_t buf = tile_iter & 1;
+      const int kappa = tile_k[tile];
+      const int p0 = tile_start[tile];
+      const int rows = min(kTileM, kofs[kappa + 1] - p0);
+      const int r = lane_grp * 32 + lane;
+      const int j = r < rows ? out_idx[p0 + r] : -1;
+      mbar_wait(smem_u32(&sh.acc_full[buf]), (tile_iter >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * acc_stride + ((uint32_t)(lane_grp * 32) << 16);
+      int col = 0;
+      for (; col + 32 <= cout; col += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + col, v);
+        if (epi) scatter32_lines(epi_stage, lane, out, cout, col, j, v);
+        else scatter32_rows(out, cout, col, j, v);
+      }
+      if (col < cout) {   // cout % 32 == 16
+        uint32_t v[16];
+        tc_ld16(taddr + col, v);
+        if (j >= 0) {
+          float* dst = out + (size_t)j * cout + col;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      tc_fence_before();
+      if (rank == 0) mbar_arrive(smem_u32(&sh.acc_empty[buf]));
+      else mbar_arrive_cluster(mapa_u32(smem_u32(&sh.acc_empty[buf]), 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // nobody exits (or frees TMEM) while the peer may still use or signal it
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+  }
+}
+
 // W[K, cin, cout] fp32  ->  packed[K][cin/32][2][cout][32]: for every (kappa, 32-channel chunk) the
 // K-major SWIZZLE_128B shared-memory image of the B operand, TF32 "hi" tile followed by the "lo"
 // residual tile - exactly what one bulk copy drops into a pipeline stage.
@@ -576,15 +901,27 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
   DGR_ARG_CHECK(tile_rows == kTileM, "tile_rows must be 128");
   DGR_ARG_CHECK(dgr_spconv_tc_supported(cin, cout), "shape not supported by the tensor-core path");
   DGR_ARG_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
-  DGR_ARG_CHECK(cluster >= 0 && cluster <= 2, "variant must be 0 (A in TMEM), 1 (A in smem) or 2 (CTA pairs)");
+  DGR_ARG_CHECK(cluster >= 0 && cluster <= 3,
+                "variant must be 0 (A in TMEM), 1 (A in smem), 2 (CTA pairs, multicast B) or 3 (cta_group::2)");
   if (n_tiles == 0) return DGR_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // gather lookahead in chunks (1..3); DGR_TC_PREFETCH overrides the default for experiments
+  static const int pd = [] {
+    const char* e = getenv("DGR_TC_PREFETCH");
+    int v = e ? atoi(e) : 1;
+    return v < 1 ? 1 : (v > 3 ? 3 : v);
+  }();
   const int stage_bytes = 2 * kATileBytes + 2 * cout * 128;
   const int n_chunks = cin / kChunk;
   int n_stages = (200 * 1024) / stage_bytes;
   if (n_stages > 4) n_stages = 4;
   if (n_stages < 2) n_stages = 2;
-  const size_t smem = sizeof(TcShared) + 1024 + (size_t)n_stages * stage_bytes;
+  const size_t smem = sizeof(TcShared) + 1024 + (size_t)n_stages * stage_bytes + kEpiStageBytes;
+  // epilogue scatter: 1 = line-coalesced through shared memory (default), 0 = one row per lane
+  static const int epi = [] {
+    const char* e = getenv("DGR_TC_EPILOGUE");
+    return e ? (atoi(e) != 0) : 1;
+  }();
   int acc_cols = 32;                       // one accumulator: power of two >= cout
   while (acc_cols < cout) acc_cols <<= 1;
   const int tmem_cols = 2 * acc_cols;      // two accumulators: epilogue overlaps the next tile
@@ -609,11 +946,38 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
     spconv_tc_at_kernel<<<grid, kThreadsTC, smem_at, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
                                                            tile_k, tile_start, n_tiles, ns, cols, n_acc, acc_cols,
                                                            passes, out);
+  } else if (cluster == 3) {
+    // cta_group::2: one M = 256 MMA per tile pair, each CTA holds half of every weight tile
+    DGR_ARG_CHECK(n_tiles % 2 == 0, "a paired tile list has an even number of tiles");
+    const int sb2 = 2 * kATileBytes + cout * 128;
+    int ns2 = (200 * 1024) / sb2;
+    if (ns2 > 4) ns2 = 4;
+    const size_t smem2 = sizeof(Tc2Shared) + 1024 + (size_t)ns2 * sb2 + kEpiStageBytes;
+    grid = sms & ~1;
+    if (grid > n_tiles) grid = n_tiles;
+    auto pair_kernel = pd == 1 ? spconv_tc_pair_kernel<1> : pd == 2 ? spconv_tc_pair_kernel<2> : spconv_tc_pair_kernel<3>;
+    DGR_CUDA_CHECK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreadsTC);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DGR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, pair_kernel, in_feat, (int)cin, weight_t, (int)cout, in_idx,
+                                      out_idx, kofs, tile_k, tile_start, (int)n_tiles, ns2, tmem_cols,
+                                      (int)passes, epi, out));
   } else if (cluster == 2) {
     // CTA pairs on two tiles of the same offset, B tiles multicast to both (paired tile list)
     DGR_ARG_CHECK(n_tiles % 2 == 0, "a paired tile list has an even number of tiles");
     grid &= ~1;
-    DGR_ENSURE_SMEM(spconv_tc_kernel<2>, smem);
+    auto k2 = pd == 1 ? spconv_tc_kernel<2, 1> : pd == 2 ? spconv_tc_kernel<2, 2> : spconv_tc_kernel<2, 3>;
+    DGR_CUDA_CHECK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreadsTC);
@@ -626,14 +990,15 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DGR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, spconv_tc_kernel<2>, in_feat, (int)cin, weight_t, (int)cout, in_idx,
+    DGR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k2, in_feat, (int)cin, weight_t, (int)cout, in_idx,
                                       out_idx, kofs, tile_k, tile_start, (int)n_tiles, n_stages, tmem_cols,
-                                      (int)passes, out));
+                                      (int)passes, epi, out));
   } else {
-    DGR_ENSURE_SMEM(spconv_tc_kernel<1>, smem);
-    spconv_tc_kernel<1><<<grid, kThreadsTC, smem, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
+    auto k1 = pd == 1 ? spconv_tc_kernel<1, 1> : pd == 2 ? spconv_tc_kernel<1, 2> : spconv_tc_kernel<1, 3>;
+    DGR_CUDA_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1<<<grid, kThreadsTC, smem, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
                                                         tile_k, tile_start, n_tiles, n_stages, tmem_cols, passes,
-                                                        out);
+                                                        epi, out);
   }
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();

@@ -110,8 +110,9 @@ def test_spconv_tensor_core(abi, D, cin, cout):
 
 @pytest.mark.parametrize('D,cin,cout', [(3, 256, 256), (3, 128, 128), (6, 64, 240), (3, 32, 32)])
 def test_spconv_tensor_core_cta_pairs(abi, D, cin, cout):
-  """2-CTA cluster variant (weight tiles multicast to both CTAs, paired tile list with empty
-  padding tiles) must equal the single-CTA kernel's result."""
+  """Every kernel variant - cta_group::2 (one M = 256 MMA per tile pair, half of each weight tile
+  per CTA), 2-CTA cluster with multicast weight tiles, A in shared memory, A in tensor memory -
+  on the paired tile list (empty padding tiles) or the plain one must match the oracle."""
   from deepglobalregistration_b200.me.coords import CoordinateManager, CoordinateMapKey
   coords = _coords(cin + 7 * cout + D, 4000, D, 10 if D == 3 else 3)
   n = len(coords)
@@ -126,7 +127,7 @@ def test_spconv_tensor_core_cta_pairs(abi, D, cin, cout):
   assert nt % 2 == 0 and nt >= km.n_tiles
   tkh = tk.cpu().numpy()[:nt]
   assert (tkh[0::2] == tkh[1::2]).all()              # both tiles of a pair share the kernel offset
-  for variant, name in ((2, '2-CTA cluster'), (1, 'A in smem'), (0, 'A in TMEM')):
+  for variant, name in ((3, 'cta_group::2'), (2, '2-CTA cluster'), (1, 'A in smem'), (0, 'A in TMEM')):
     for rep in range(2):
       out = torch.zeros(n, cout, device='cuda')
       abi.spconv_tc_fwd(feat.cuda(), Wt, km, out, passes=3, cluster=variant)
