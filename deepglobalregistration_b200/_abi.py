@@ -397,10 +397,12 @@ def pack_weight_tf32(weight, K, cin, cout):
   return packed
 
 
-# kernel variant of the tensor-core convolution: 1 = both operands in shared memory (default,
-# fastest measured), 0 = A operand in tensor memory, 2 = 1 with CTA pairs and multicast weight
-# tiles.  All three are parity-tested; all three run at the same speed on the wide layers, which
-# is how the L2->SM ingress bound was identified.
+# kernel variant of the tensor-core convolution: 1 = one CTA per tile, both operands in shared
+# memory (default), 0 = A operand in tensor memory, 2 = CTA pairs with multicast weight tiles,
+# 3 = cta_group::2 (one M = 256 MMA per tile pair, half of every weight tile per CTA; used for
+# cout >= TC_PAIR_MIN_COUT, else 1).  All four are parity-tested.  With the line-coalesced epilogue
+# variant 3 is ~6 % faster on the wide layers (profiles/r01_spconv_tc_experiments.txt); it stays
+# opt-in until the whole GPU suite has run with it.
 TC_VARIANT = int(os.environ.get('DGR_TC_VARIANT', '1'))
 TC_PAIR_MIN_COUT = int(os.environ.get('DGR_TC_PAIR_MIN_COUT', '128'))
 
