@@ -120,3 +120,19 @@ def test_two_ranks_agree_with_one(tmp_path):
   r0, r1 = torch.load(tmp_path / 'stats0.pt', weights_only=False), torch.load(tmp_path / 'stats1.pt', weights_only=False)
   assert np.array_equal(r0[:, [0, 4]], one[:, [0, 4]]) and np.array_equal(r0[:, :3], r1[:, :3])
   np.testing.assert_allclose(r0[:, 1:3], one[:, 1:3], atol=1e-9)
+
+
+def test_metric_and_trajectory_reader_match_reference_golden():
+  """tests/golden/reference_io.npz was produced by the reference's own util/file.py::read_trajectory
+  and scripts/test_3dmatch.py::rte_rre (tests/golden/make_golden_io.py)."""
+  here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+  gold = np.load(os.path.join(here, 'reference_io.npz'))
+  traj = dio.read_trajectory(os.path.join(here, 'sample_gt.log'))
+  assert np.array_equal(np.array([t.metadata for t in traj]), gold['traj_meta'])
+  assert np.array_equal(np.stack([t.pose for t in traj]), gold['traj_pose'])           # bit-exact parse
+  for Tp, Tg, want in zip(gold['metric_pred'], gold['metric_gt'], gold['metric_out']):
+    got = ev.rte_rre(Tp, Tg, 0.3, 15)
+    assert got[0] == want[0]
+    np.testing.assert_allclose(got[1:], want[1:], rtol=1e-12, atol=1e-12)
+  assert np.array_equal(ev.rte_rre(None, gold['metric_gt'][0], 0.3, 15), gold['metric_none'])
+  assert 0 < gold['metric_out'][:, 0].sum() < len(gold['metric_out'])                  # both outcomes covered
