@@ -10,6 +10,12 @@ Pair sources:
 * a 3DMatch test tree: ``<root>/<scene>/cloud_bin_<i>.ply`` and ``<root>/<scene>-evaluation/gt.log``
   (dataloader/threedmatch_loader.py:167-196); gt.log holds the pose of fragment j in fragment i's
   frame, so the pose register(cloud_i, cloud_j) must return is its inverse (scripts/test_3dmatch.py:107);
+* a KITTI odometry tree: ``<root>/dataset/sequences/<dd>/velodyne/<tttttt>.bin`` and
+  ``<root>/dataset/poses/<dd>.txt``; pairs = frames at least 10 m apart chosen the way
+  dataloader/kitti_loader.py:229-279 chooses them, ground truth from the odometry poses and the
+  velodyne-to-camera calibration (:66-78, :147-148).  The reference additionally polishes that pose
+  with a 200-iteration ICP and caches it (:139-160); that refinement is NOT applied here, so RTE / RRE
+  carry the odometry's own error (a few cm) - fine for the 0.6 m / 5 deg success criterion;
 * a pair list: one pair per line, ``file0 file1 [16 numbers = row-major 4x4 mapping file0 into file1's
   frame] [group]``, any format io.read_points understands (KITTI .bin, .npz, .ply ...).
 
@@ -56,6 +62,61 @@ def threedmatch_pairs(root, scenes=None, ext='.ply'):
       i, j = cp.metadata[0], cp.metadata[1]
       pairs.append(Pair(os.path.join(root, scene, f'cloud_bin_{i}{ext}'),
                         os.path.join(root, scene, f'cloud_bin_{j}{ext}'), np.linalg.inv(cp.pose), scene))
+  return pairs
+
+
+# velodyne -> camera-0 calibration the reference hard-codes (dataloader/kitti_loader.py:66-78)
+KITTI_VELO2CAM = np.array([
+    [7.533745e-03, -9.999714e-01, -6.166020e-04, -4.069766e-03],
+    [1.480249e-02, 7.280733e-04, -9.998902e-01, -7.631618e-02],
+    [9.998621e-01, 7.523790e-03, 1.480755e-02, -2.717806e-01],
+    [0.0, 0.0, 0.0, 1.0]])
+KITTI_TEST_DRIVES = (8, 9, 10)                  # dataloader/split/test_kitti.txt
+KITTI_SKIPPED = {(8, 15, 58)}                   # "problematic sequence", dataloader/kitti_loader.py:275-279
+
+
+def kitti_poses(root, drive):
+  """[n_frames, 4, 4] camera-0 poses of a drive (poses/<dd>.txt: 12 numbers per line)."""
+  odo = np.loadtxt(os.path.join(root, 'dataset', 'poses', f'{drive:02d}.txt'), ndmin=2)
+  P = np.tile(np.eye(4), (len(odo), 1, 1))
+  P[:, :3, :] = odo.reshape(-1, 3, 4)
+  return P
+
+
+def kitti_gt_pose(P0, P1):
+  """Pose mapping the velodyne frame of scan 0 into that of scan 1: V^-1 P1^-1 P0 V - what the
+  reference computes (in transposed form) at dataloader/kitti_loader.py:147-148."""
+  V = KITTI_VELO2CAM
+  return np.linalg.inv(V) @ np.linalg.inv(P1) @ P0 @ V
+
+
+def kitti_pairs(root, drives=KITTI_TEST_DRIVES, min_dist=10.0):
+  """The test pairs of KITTINMPairDataset (dataloader/kitti_loader.py:229-279): walk each drive,
+  pair the current frame with the frame just before the first one (within 100 frames) that is
+  more than `min_dist` metres away, continue after the partner."""
+  pairs = []
+  for drive in drives:
+    vel = os.path.join(root, 'dataset', 'sequences', f'{drive:02d}', 'velodyne')
+    frames = sorted(int(f[:-4]) for f in os.listdir(vel) if f.endswith('.bin'))
+    if not frames:
+      raise FileNotFoundError(f'no scans under {vel}')
+    have = set(frames)
+    P = kitti_poses(root, drive)
+    pos = P[:, :3, 3]
+    cur = frames[0]
+    while cur in have:
+      far = np.flatnonzero(np.linalg.norm(pos[cur:cur + 100] - pos[cur], axis=1) > min_dist)
+      if len(far) == 0:
+        cur += 1
+        continue
+      nxt = int(far[0]) + cur - 1
+      if nxt not in have:
+        cur += 1                                   # (the reference would spin here; frames are contiguous in KITTI)
+        continue
+      if (drive, cur, nxt) not in KITTI_SKIPPED:
+        pairs.append(Pair(os.path.join(vel, f'{cur:06d}.bin'), os.path.join(vel, f'{nxt:06d}.bin'),
+                          kitti_gt_pose(P[cur], P[nxt]), f'drive{drive:02d}'))
+      cur = nxt + 1
   return pairs
 
 
@@ -126,6 +187,8 @@ def main(argv=None):
   ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
   src = ap.add_mutually_exclusive_group(required=True)
   src.add_argument('--threed_match_dir', help='3DMatch test tree (scene folders + <scene>-evaluation/gt.log)')
+  src.add_argument('--kitti_dir', help='KITTI odometry root (contains dataset/sequences, dataset/poses); '
+                   'use --success_rte_thresh 0.6 --success_rre_thresh 5 (scripts/test_kitti.py:33-34)')
   src.add_argument('--pair_list', help='text file: file0 file1 [16 numbers] [group] per line')
   ap.add_argument('--weights', required=True)
   ap.add_argument('--clip_weight_thresh', type=float, default=0.05)
@@ -145,7 +208,12 @@ def main(argv=None):
   cfg = argparse.Namespace(weights=args.weights, clip_weight_thresh=args.clip_weight_thresh, verbose=False)
   dgr = DeepGlobalRegistration(cfg, device=torch.device('cuda', local))
   dgr.use_icp = not args.no_icp
-  pairs = threedmatch_pairs(args.threed_match_dir) if args.threed_match_dir else read_pair_list(args.pair_list)
+  if args.threed_match_dir:
+    pairs = threedmatch_pairs(args.threed_match_dir)
+  elif args.kitti_dir:
+    pairs = kitti_pairs(args.kitti_dir)
+  else:
+    pairs = read_pair_list(args.pair_list)
   result = evaluate(dgr, pairs, args.success_rte_thresh, args.success_rre_thresh,
                     log=print if rank == 0 else None)
   if rank == 0:

@@ -136,3 +136,32 @@ def test_metric_and_trajectory_reader_match_reference_golden():
     np.testing.assert_allclose(got[1:], want[1:], rtol=1e-12, atol=1e-12)
   assert np.array_equal(ev.rte_rre(None, gold['metric_gt'][0], 0.3, 15), gold['metric_none'])
   assert 0 < gold['metric_out'][:, 0].sum() < len(gold['metric_out'])                  # both outcomes covered
+
+
+def test_kitti_pairs_and_ground_truth_match_reference_golden(tmp_path):
+  """tests/golden/reference_kitti.npz: file list and ground-truth poses produced by the reference's own
+  KITTINMPairDataset on a synthetic odometry tree (tests/golden/make_golden_kitti.py)."""
+  gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_kitti.npz'))
+  os.makedirs(tmp_path / 'dataset' / 'poses')
+  for drive in (8, 9, 10):
+    P = gold[f'poses_{drive:02d}']
+    np.savetxt(tmp_path / 'dataset' / 'poses' / f'{drive:02d}.txt', P, fmt='%.9e')
+    vel = tmp_path / 'dataset' / 'sequences' / f'{drive:02d}' / 'velodyne'
+    os.makedirs(vel)
+    for k in range(len(P) - 1):                       # one pose more than scans (see the generator)
+      (vel / f'{k:06d}.bin').write_bytes(b'')
+  np.testing.assert_allclose(ev.KITTI_VELO2CAM, gold['velo2cam_T'].T, rtol=0, atol=0)
+  pairs = ev.kitti_pairs(str(tmp_path))
+  got = [(int(p.group[-2:]), int(os.path.basename(p.file0)[:-4]), int(os.path.basename(p.file1)[:-4])) for p in pairs]
+  assert got == [tuple(int(x) for x in f) for f in gold['files']]
+  for p, M in zip(pairs, gold['M']):
+    np.testing.assert_allclose(p.T_gt, M, atol=1e-10)
+    assert np.allclose(p.T_gt[:3, :3] @ p.T_gt[:3, :3].T, np.eye(3), atol=1e-6)
+  # every pair is 10..~11.5 m apart (the frame BEFORE the first one farther than 10 m), same drive
+  d = [np.linalg.norm(p.T_gt[:3, 3]) for p in pairs]
+  assert 8.0 < min(d) and max(d) <= 10.0 + 1e-9
+  assert {p.group for p in pairs} == {'drive08', 'drive09', 'drive10'}
+  # a drive with no scans is an error, not an empty result
+  os.makedirs(tmp_path / 'empty' / 'dataset' / 'sequences' / '08' / 'velodyne')
+  with pytest.raises(FileNotFoundError):
+    ev.kitti_pairs(str(tmp_path / 'empty'), drives=(8,))
