@@ -9,6 +9,8 @@ all 3^D convolutions except conv1 (conv1_kernel_size) and the two 1x1 layers;
 ``conv()`` never passes a bias (model/residual_block.py:38-44), only ``final``
 has one (model/resunet.py:589-596).
 
+The GRAPH is pinned: tests/test_oracle_graph_vs_reference.py runs the reference's unmodified
+model/resunet.py on the CPU over oracle/me_cpu.py and requires identical outputs.
 PARITY UNPINNED for the sparse operators themselves, see oracle/sparse_ops.py.
 """
 import torch
