@@ -42,7 +42,8 @@ class SparseTensor:
     coordinate_manager = coords_manager if coordinate_manager is None else coordinate_manager
     self.F = features
     if coordinate_manager is None:
-      coordinate_manager = so.CoordinateMaps(np.asarray(coordinates))
+      coordinate_manager = so.CoordinateMaps(coordinates.cpu().numpy() if isinstance(coordinates, torch.Tensor)
+                                             else np.asarray(coordinates))
       coordinate_map_key = 1
     self.coordinate_manager, self.coordinate_map_key = coordinate_manager, coordinate_map_key   # key = tensor stride
 
@@ -130,6 +131,24 @@ def _relu(x):
   return x._like(torch.relu(x.F))
 
 
+def sparse_quantize(coordinates, features=None, labels=None, return_index=False, **kw):
+  """ME 0.5 form as the reference uses it (core/deep_global_registration.py:152): floor the
+  (already divided) coordinates, keep the first row of every voxel, indices ascending.
+  -> (unique int coordinates, index)."""
+  assert features is None and labels is None
+  is_tensor = isinstance(coordinates, torch.Tensor)
+  c = np.floor(coordinates.numpy() if is_tensor else np.asarray(coordinates)).astype(np.int32)
+  sel, _ = so._first_occurrence(c)
+  uniq = torch.from_numpy(c[sel]) if is_tensor else c[sel]
+  if return_index:
+    return uniq, (torch.from_numpy(sel) if is_tensor else sel)
+  return uniq
+
+
+def batched_coordinates(coords, dtype=torch.int32, device=None):
+  return torch.from_numpy(so.batched_coordinates([np.asarray(c) for c in coords])).to(dtype)
+
+
 def _unsupported(name):
   class _Missing(nn.Module):
     def __init__(self, *a, **k):
@@ -152,6 +171,8 @@ def module():
   mef.relu = _relu
   utils = types.ModuleType('MinkowskiEngine.utils')
   utils.kaiming_normal_ = lambda *a, **k: None
+  utils.sparse_quantize = sparse_quantize
+  utils.batched_coordinates = batched_coordinates
   me.MinkowskiFunctional, me.utils = mef, utils
   return me, mef, utils
 

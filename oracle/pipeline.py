@@ -4,6 +4,10 @@ the CPU, stage by stage, following DeepGlobalRegistration.register()
 the RANSAC safeguard (:302-315, oracle/ransac.py) when the weight sum is below
 the gate, then optionally the ICP fine-tune (:317-322, oracle/icp.py).
 
+PINNED against the reference's own register() run on the CPU over oracle-backed stand-ins
+for MinkowskiEngine / open3d (tests/test_oracle_pipeline_vs_reference.py); the sparse operators
+and ICP underneath remain unpinned restatements (see their headers).
+
 Each stage returns its tensors so that GPU parity tests can tap in anywhere and
 feed the oracle's outputs of stage k into the CUDA stage k+1 (stage-isolated
 parity), see tests/test_gpu_pipeline.py.

@@ -1,0 +1,94 @@
+"""oracle/pipeline.py::register against the reference's OWN DeepGlobalRegistration.register():
+core/deep_global_registration.py, core/knn.py, core/registration.py, model/*.py, util/*.py are
+imported unmodified from /root/reference and run end to end on the CPU, with
+* MinkowskiEngine  -> oracle/me_cpu.py (sparse operators of oracle/sparse_ops.py),
+* open3d           -> the I/O stand-in of shims.py + registration_icp backed by oracle/icp.py.
+The sparse operators and ICP are therefore the oracle's on both sides; what this pins is everything
+else the oracle restates by hand: the order of the stages, dtypes, voxelisation and re-flooring, the
+6-D coordinate assembly, feature types, the sigmoid / clip / weight-sum gate and its thresholds, the
+arguments handed to GlobalRegistration and to ICP.  Needs /root/reference: skipped elsewhere."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from deepglobalregistration_b200 import shims
+from deepglobalregistration_b200 import synthetic as syn
+from oracle import icp as oicp
+from oracle import me_cpu
+from oracle import pipeline as op
+
+REF = '/root/reference'
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'core')), reason='reference tree not present')
+_REF_PACKAGES = ('model', 'core', 'util')
+
+
+@pytest.fixture
+def reference_dgr(monkeypatch):
+  """The reference's DeepGlobalRegistration class, importable on a CPU-only box."""
+  restore_me = me_cpu.install()
+  o3d = shims._open3d_stub()
+  o3d.pipelines = types.ModuleType('open3d.pipelines')
+  o3d.pipelines.registration = types.ModuleType('open3d.pipelines.registration')
+
+  def registration_icp(source, target, max_correspondence_distance, init=np.eye(4), *a, **k):
+    T, info = oicp.icp_point_to_point(np.asarray(source.points), np.asarray(target.points),
+                                      max_correspondence_distance, init)
+    return types.SimpleNamespace(transformation=T, fitness=info['fitness'], inlier_rmse=info['inlier_rmse'])
+  o3d.pipelines.registration.registration_icp = registration_icp
+  saved = {k: sys.modules.get(k) for k in list(sys.modules)
+           if k == 'open3d' or k.startswith('open3d.') or k.split('.')[0] in _REF_PACKAGES}
+  for k in saved:
+    del sys.modules[k]
+  sys.modules['open3d'] = o3d
+  sys.path.insert(0, REF)
+  real_load = torch.load
+  monkeypatch.setattr(torch, 'load', lambda f, *a, **k: real_load(f, *a, **dict(k, weights_only=False)))
+  cwd = os.getcwd()
+  try:
+    from core.deep_global_registration import DeepGlobalRegistration
+    yield DeepGlobalRegistration
+  finally:
+    os.chdir(cwd)
+    sys.path.remove(REF)
+    for k in [k for k in sys.modules if k == 'open3d' or k.startswith('open3d.') or k.split('.')[0] in _REF_PACKAGES]:
+      del sys.modules[k]
+    sys.modules.update({k: v for k, v in saved.items() if v is not None})
+    restore_me()
+
+
+@pytest.mark.parametrize('feature_type,dtype', [('ones', np.float64), ('coords', np.float32)])
+def test_reference_register_equals_oracle_pipeline(reference_dgr, tmp_path, feature_type, dtype, capsys):
+  state = syn.make_checkpoint(1, inlier_feature_type=feature_type)
+  path = tmp_path / 'ckpt.pth'
+  torch.save(state, path)
+  xyz0, xyz1, _ = syn.room_pair(7, n_raw=5000, extent=(1.2, 1.0, 0.8))
+  xyz0, xyz1 = xyz0.astype(dtype), xyz1.astype(dtype)
+  cfg = types.SimpleNamespace(weights=str(path), clip_weight_thresh=0.05)
+  dgr = reference_dgr(cfg, device=torch.device('cpu'))
+  assert dgr.use_icp is True and dgr.voxel_size == state['config']['voxel_size']
+  # tap A: the pose before ICP
+  dgr.use_icp = False
+  T_ref = dgr.register(xyz0, xyz1)
+  T_o, taps = op.register(state, xyz0, xyz1, clip_weight_thresh=0.05)
+  assert taps['branch'] == 'procrustes'
+  printed = capsys.readouterr().out
+  assert f"=> Weighted sum {taps['wsum']:.2f} >=" in printed           # same gate value, same branch
+  te, re = syn.rte_rre(T_ref, T_o)
+  assert te <= 1e-3 and re <= 1e-3, (te, re, taps['refine'])
+  # stage taps through the reference's own methods
+  p0, c0, f0 = dgr.preprocess(xyz0)
+  assert np.array_equal(c0.numpy(), taps['coords0']) and np.array_equal(p0.numpy(), taps['xyz0'])
+  assert p0.dtype == torch.float32 and c0.dtype == torch.int32 and tuple(f0.shape) == (len(c0), 1)
+  with torch.no_grad():
+    F0 = dgr.fcgf_feature_extraction(f0, c0)
+  assert float((F0 - taps['feat0']).abs().max()) <= 1e-6
+  # tap B: the literal return value (ICP on)
+  dgr.use_icp = True
+  T_ref = dgr.register(xyz0, xyz1)
+  T_o, taps = op.register(state, xyz0, xyz1, clip_weight_thresh=0.05, use_icp=True)
+  te, re = syn.rte_rre(T_ref, T_o)
+  assert te <= 1e-3 and re <= 1e-3, (te, re, taps['icp'])
