@@ -4,7 +4,8 @@ Scan pairs are independent (the reference's evaluation loops are per pair,
 scripts/test_3dmatch.py:99-127, scripts/test_kitti.py:67-84), so the path shards with no
 data-path collective: every rank holds a replica of both checkpoints and registers pairs
 rank, rank + W, ...; the only exchange is one all-gather of the per-pair results
-([4x4 pose, weight sum, iterations, branch, milliseconds] = 20 floats) at the end - NCCL over
+([4x4 pose, weight sum, iterations, branch, milliseconds] = 20 float64: the pose keeps the
+precision register() returns) at the end - NCCL over
 NVLink on GPUs, gloo in the CPU tests."""
 import time
 
@@ -22,7 +23,7 @@ def shard_indices(n_pairs, rank, world):
 
 
 def pack_result(T, wsum=0.0, iterations=0, branch=None, ms=0.0):
-  row = np.zeros(RESULT_WIDTH, np.float32)
+  row = np.zeros(RESULT_WIDTH, np.float64)
   row[:16] = np.asarray(T, np.float64).reshape(16)
   row[16:] = (wsum, iterations, BRANCH_CODE.get(branch, -1.0), ms)
   return row
@@ -34,10 +35,10 @@ def gather_results(local_rows, n_pairs, device=None):
   world = dist.get_world_size() if dist.is_initialized() else 1
   rank = dist.get_rank() if dist.is_initialized() else 0
   per_rank = (n_pairs + world - 1) // world
-  buf = torch.zeros(per_rank, RESULT_WIDTH, dtype=torch.float32)
+  buf = torch.zeros(per_rank, RESULT_WIDTH, dtype=torch.float64)
   mine = shard_indices(n_pairs, rank, world)
   if len(mine):
-    buf[:len(mine)] = torch.from_numpy(np.stack(local_rows).astype(np.float32))
+    buf[:len(mine)] = torch.from_numpy(np.stack(local_rows).astype(np.float64))
   if device is not None:
     buf = buf.to(device)
   if world > 1:
@@ -45,7 +46,7 @@ def gather_results(local_rows, n_pairs, device=None):
     dist.all_gather(parts, buf)
   else:
     parts = [buf]
-  out = torch.zeros(n_pairs, RESULT_WIDTH, dtype=torch.float32)
+  out = torch.zeros(n_pairs, RESULT_WIDTH, dtype=torch.float64)
   for r, part in enumerate(parts):
     idx = shard_indices(n_pairs, r, world)
     out[idx] = part[:len(idx)].cpu()
@@ -63,7 +64,7 @@ def _cloud(item):
 
 def register_pairs(dgr, pairs, device=None):
   """Register this rank's share of `pairs` ([(xyz0, xyz1), ...]; members may be file paths) with
-  `dgr` and gather all results.  Returns [len(pairs), 20] float32, identical on every rank.  The
+  `dgr` and gather all results.  Returns [len(pairs), 20] float64, identical on every rank.  The
   milliseconds column times register() only, not the file reads."""
   world = dist.get_world_size() if dist.is_initialized() else 1
   rank = dist.get_rank() if dist.is_initialized() else 0
