@@ -56,7 +56,7 @@ def base_config(n_gpus):
           'fcgf_model': 'ResUNetBN2C(D=3,conv1_k=7)', 'inlier_model': 'ResUNetBN2C(D=6,conv1_k=3)',
           'conv_arithmetic': 'tcgen05 3xTF32 (fp32-accurate) + fp32 FFMA for conv1',
           'parallelism': f'pair-sharded dp{n_gpus}', 'pairs_per_step_per_gpu': 1,
-          'excluded_on_both_arms': 'ICP fine-tune (built, use_icp=True, not part of the benchmarked unit) and the RANSAC safeguard (not built)',
+          'excluded_on_both_arms': 'ICP fine-tune and RANSAC safeguard (both built; the benchmarked unit is SURVEY 8(d)\'s: through the SE(3) refinement, and the benchmark pairs take the Procrustes branch)',
           'l2_policy': 'inputs larger than L2: every step streams the 944 MB inlier-net weights '
                        '(L2 = 126 MB) and cycles through %d distinct pairs' % POOL}
 
