@@ -8,8 +8,8 @@
 One "step" = one full register() of one synthetic 3DMatch-shape scan pair (BASELINE.json
 configs[1]/[3] shape: ~50k voxels per cloud at 0.05 m, FCGF feature dim 32, ResUNetBN2C for
 both networks): voxelise x2 -> FCGF x2 -> feature kNN -> 6-D inlier network -> weights ->
-weighted Procrustes + SE(3) refinement.  ICP / RANSAC (open3d) are outside the built path
-on both arms.  Pairs are independent: each rank registers its own pairs (weak scaling) and
+weighted Procrustes + SE(3) refinement (SURVEY 8(d)'s unit).  The ICP fine-tune and the RANSAC
+safeguard are built but outside the benchmarked unit on both arms.  Pairs are independent: each rank registers its own pairs (weak scaling) and
 the poses are all-gathered over NCCL at the end of the timed region.
 
 Prints ONE JSON line (rank 0).  `value` = pairs/s with the raw scans resident in HBM;
