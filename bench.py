@@ -413,7 +413,7 @@ def run_ours(args):
   h2d = int(sum(a.nbytes + b.nbytes for a, b, _ in pairs_host) / POOL)
   fixed_d2h = 2 * 8 + 8 + 9 * 4 + 8 + 64     # counts, spec flags, coarse-map sizes, wsum, pose
   line = {'metric': 'scan_pairs_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K,
-          'warmup': max(args.warmup, 3) * POOL + POOL + 2 * K, 'ms_per_step': res['ms'] / K, 'higher_is_better': True,
+          'warmup': args.warmup, 'warmup_steps_run': max(args.warmup, 3) * POOL + POOL + 2 * K, 'ms_per_step': res['ms'] / K, 'higher_is_better': True,
           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
           'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d,
                   'd2h_bytes_per_step': int(res_e2e['d2h'] / K) + fixed_d2h,
