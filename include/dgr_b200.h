@@ -160,7 +160,12 @@ int32_t dgr_spconv_fwd(const float* in_feat, int32_t cin, const float* weight, i
  * 1 = both operands in shared memory (default); 0 = A operand split straight into tensor memory
  * (tcgen05.st), shared memory holds only the weight slabs; 2 = as 1 with thread-block clusters of
  * two CTAs that work on two tiles of the same offset and receive each weight tile by ONE multicast
- * bulk copy (needs the paired tile list of dgr_kernel_map_tiles(pair = 1)). */
+ * bulk copy; 3 = tcgen05 cta_group::2: the CTA pair issues ONE M = 256 MMA per two tiles of the same
+ * offset and every CTA holds only half of each weight tile (2 and 3 need the paired tile list of
+ * dgr_kernel_map_tiles(pair = 1)).  All variants scatter through a shared-memory transpose so that a
+ * warp instruction writes whole 128-byte lines of the output rows.  Process-level tuning knobs read
+ * once from the environment: DGR_TC_PREFETCH (gather lookahead in chunks, 1..3, default 1),
+ * DGR_TC_EPILOGUE (0 = scatter one row per lane, the pre-transposition epilogue; default 1). */
 int32_t dgr_spconv_tc_supported(int32_t cin, int32_t cout);
 int32_t dgr_pack_weight_tf32(const float* w, int32_t K, int32_t cin, int32_t cout, float* packed, void* stream);
 int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight_t, int32_t cout,
