@@ -99,12 +99,24 @@ def _check(status, name):
 
 _FN = {}
 
+# When set to a list, every ABI call is bracketed by CUDA events on torch's current stream and appends
+# (entry point, start event, end event): tools/abi_profile.py turns that into warm, in-context GPU time
+# per entry point (ncu's per-launch times are cold-cache and serialised).  None = no overhead.
+CALL_PROFILE = None
+
 
 def call(name, *args):
   fn = _FN.get(name)
   if fn is None:
     fn = _FN[name] = getattr(lib(), name)
-  status = fn(*args)
+  if CALL_PROFILE is not None:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    status = fn(*args)
+    e1.record()
+    CALL_PROFILE.append((name, e0, e1))
+  else:
+    status = fn(*args)
   if status != 0:
     _check(status, name)
 
