@@ -34,7 +34,11 @@ def reference_dgr(monkeypatch):
   o3d.pipelines = types.ModuleType('open3d.pipelines')
   o3d.pipelines.registration = types.ModuleType('open3d.pipelines.registration')
 
+  icp_calls = []
+
   def registration_icp(source, target, max_correspondence_distance, init=np.eye(4), *a, **k):
+    icp_calls.append(dict(init=np.array(init), max_dist=max_correspondence_distance, n_source=len(source.points),
+                          n_target=len(target.points)))
     T, info = oicp.icp_point_to_point(np.asarray(source.points), np.asarray(target.points),
                                       max_correspondence_distance, init)
     return types.SimpleNamespace(transformation=T, fitness=info['fitness'], inlier_rmse=info['inlier_rmse'])
@@ -45,11 +49,18 @@ def reference_dgr(monkeypatch):
     del sys.modules[k]
   sys.modules['open3d'] = o3d
   sys.path.insert(0, REF)
+  # the reference calls torch.load(config.weights) on a path that must exist; writing and re-reading the
+  # 1 GB synthetic checkpoint costs minutes of page-cache traffic, so the patched loader hands back the
+  # in-memory dict registered for that path (the file-level boundary is covered by the GPU tests)
   real_load = torch.load
-  monkeypatch.setattr(torch, 'load', lambda f, *a, **k: real_load(f, *a, **dict(k, weights_only=False)))
+  preloaded = {}
+  monkeypatch.setattr(torch, 'load', lambda f, *a, **k: preloaded[str(f)] if str(f) in preloaded
+                      else real_load(f, *a, **dict(k, weights_only=False)))
   cwd = os.getcwd()
   try:
     from core.deep_global_registration import DeepGlobalRegistration
+    DeepGlobalRegistration.icp_calls = icp_calls          # what the reference handed to open3d
+    DeepGlobalRegistration.preloaded = preloaded
     yield DeepGlobalRegistration
   finally:
     os.chdir(cwd)
@@ -64,21 +75,26 @@ def reference_dgr(monkeypatch):
 def test_reference_register_equals_oracle_pipeline(reference_dgr, tmp_path, feature_type, dtype, capsys):
   state = syn.make_checkpoint(1, inlier_feature_type=feature_type)
   path = tmp_path / 'ckpt.pth'
-  torch.save(state, path)
+  path.write_bytes(b'')
+  reference_dgr.preloaded[str(path)] = state
   xyz0, xyz1, _ = syn.room_pair(7, n_raw=5000, extent=(1.2, 1.0, 0.8))
   xyz0, xyz1 = xyz0.astype(dtype), xyz1.astype(dtype)
   cfg = types.SimpleNamespace(weights=str(path), clip_weight_thresh=0.05)
   dgr = reference_dgr(cfg, device=torch.device('cpu'))
   assert dgr.use_icp is True and dgr.voxel_size == state['config']['voxel_size']
-  # tap A: the pose before ICP
-  dgr.use_icp = False
+  # one run with the reference's default (use_icp = True); the pose it hands to open3d's ICP is tap A
   T_ref = dgr.register(xyz0, xyz1)
-  T_o, taps = op.register(state, xyz0, xyz1, clip_weight_thresh=0.05)
+  T_o, taps = op.register(state, xyz0, xyz1, clip_weight_thresh=0.05, use_icp=True)
   assert taps['branch'] == 'procrustes'
   printed = capsys.readouterr().out
   assert f"=> Weighted sum {taps['wsum']:.2f} >=" in printed           # same gate value, same branch
-  te, re = syn.rte_rre(T_ref, T_o)
+  call, = reference_dgr.icp_calls
+  assert call['max_dist'] == 2 * dgr.voxel_size and call['n_source'] == len(taps['coords0']) \
+      and call['n_target'] == len(taps['coords1'])
+  te, re = syn.rte_rre(call['init'], taps['T_refined'])                 # tap A: before ICP
   assert te <= 1e-3 and re <= 1e-3, (te, re, taps['refine'])
+  te, re = syn.rte_rre(T_ref, T_o)                                      # tap B: the literal return value
+  assert te <= 1e-3 and re <= 1e-3, (te, re, taps['icp'])
   # stage taps through the reference's own methods
   p0, c0, f0 = dgr.preprocess(xyz0)
   assert np.array_equal(c0.numpy(), taps['coords0']) and np.array_equal(p0.numpy(), taps['xyz0'])
@@ -86,9 +102,3 @@ def test_reference_register_equals_oracle_pipeline(reference_dgr, tmp_path, feat
   with torch.no_grad():
     F0 = dgr.fcgf_feature_extraction(f0, c0)
   assert float((F0 - taps['feat0']).abs().max()) <= 1e-6
-  # tap B: the literal return value (ICP on)
-  dgr.use_icp = True
-  T_ref = dgr.register(xyz0, xyz1)
-  T_o, taps = op.register(state, xyz0, xyz1, clip_weight_thresh=0.05, use_icp=True)
-  te, re = syn.rte_rre(T_ref, T_o)
-  assert te <= 1e-3 and re <= 1e-3, (te, re, taps['icp'])
