@@ -102,3 +102,25 @@ def test_reference_register_equals_oracle_pipeline(reference_dgr, tmp_path, feat
   with torch.no_grad():
     F0 = dgr.fcgf_feature_extraction(f0, c0)
   assert float((F0 - taps['feat0']).abs().max()) <= 1e-6
+
+
+def test_public_surface_matches_the_reference_class(reference_dgr):
+  """Same public methods with the same parameter names (and defaults where the reference has them) on
+  deepglobalregistration_b200's DeepGlobalRegistration - the drop-in boundary of SURVEY.md 8(b)."""
+  import inspect
+
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration as Ours
+  ref_methods = {n: f for n, f in inspect.getmembers(reference_dgr, inspect.isfunction) if not n.startswith('_') or n == '__init__'}
+  assert set(ref_methods) == {'__init__', 'preprocess', 'fcgf_feature_extraction', 'fcgf_feature_matching',
+                              'inlier_feature_generation', 'inlier_prediction', 'safeguard_registration', 'register'}
+  for name, f in ref_methods.items():
+    ours = getattr(Ours, name, None)
+    assert ours is not None, f'missing method {name}'
+    want = inspect.signature(f).parameters
+    got = inspect.signature(ours).parameters
+    public = [p for p in got if not p.startswith('_')]          # ours may add private keyword-only helpers
+    assert public == list(want), (name, public, list(want))
+    for p in want:
+      if want[p].default is not inspect.Parameter.empty and name != '__init__':
+        assert got[p].default == want[p].default, (name, p)
+  assert str(inspect.signature(Ours.__init__).parameters['device'].default) == 'cuda'
