@@ -40,6 +40,8 @@ WORKLOAD = '3dmatch_shape_pair_register'
 N_RAW = 250_000               # raw points per scan -> ~50k voxels at 0.05 m
 SAMPLE_N_RAW = 8_000          # CPU sample: same generator, ~4k voxels per cloud
 SAMPLE_EXTENT = (1.5, 1.2, 1.0)
+REF_TIME_BUDGET_S = 180       # --impl reference: W + K sample pairs must fit this
+REF_MIN_N_RAW = 1500          # ... but never fewer raw points than this per scan
 VOXEL = 0.05
 POOL = 3                      # distinct pairs per rank, cycled over the steps
 
@@ -193,11 +195,11 @@ def cpu_threads():
   return CPU_THREADS
 
 
-def cpu_sample_time(state, seed, reps=1):
+def cpu_sample_time(state, seed, reps=1, n_raw=SAMPLE_N_RAW):
   """Seconds per pair of the CPU oracle on the bounded sample."""
   from oracle import pipeline as op
   cpu_threads()
-  xyz0, xyz1, _ = syn.room_pair(seed, n_raw=SAMPLE_N_RAW, extent=SAMPLE_EXTENT)
+  xyz0, xyz1, _ = syn.room_pair(seed, n_raw=n_raw, extent=SAMPLE_EXTENT)
   ts, info = [], {}
   for _ in range(reps):
     t = time.perf_counter()
@@ -207,8 +209,8 @@ def cpu_sample_time(state, seed, reps=1):
   return float(np.median(ts)), info
 
 
-def sample_desc(info):
-  return (f'1 pair of the same generator at {SAMPLE_N_RAW} raw points/scan -> N0={info["n0"]}, '
+def sample_desc(info, n_raw=SAMPLE_N_RAW):
+  return (f'1 pair of the same generator at {n_raw} raw points/scan -> N0={info["n0"]}, '
           f'N1={info["n1"]} voxels (the workload has ~51k/~40k); pairs/s of the SAMPLE, not extrapolated; '
           'CPU path = oracle port (torch-CPU index_select/mm/index_add per kernel offset, the algorithm '
           "of MinkowskiEngine's CPU backend) + restated kNN / Procrustes / Adam refinement")
@@ -221,22 +223,38 @@ def run_reference(args):
   state = syn.make_checkpoint(0)
   cores = cpu_threads()
   log(f'[bench] reference arm: {cores} threads (nproc {os.cpu_count()}, usable {effective_cpus()})')
-  for i in range(args.warmup):
-    cpu_sample_time(state, 100 + i)
+  # the whole run (W warm-up + K timed sample pairs) has to end within a few minutes whatever K is:
+  # the first warm-up pair is the probe; if K + W pairs of that size would not fit the budget, the
+  # sample shrinks (time is ~linear in the number of voxels) - the actual sample is reported
+  n_raw = SAMPLE_N_RAW
+  t_probe, _ = cpu_sample_time(state, 100)
+  todo = args.steps + max(args.warmup - 1, 0)
+  if t_probe * todo > REF_TIME_BUDGET_S:
+    n_raw = max(REF_MIN_N_RAW, int(SAMPLE_N_RAW * REF_TIME_BUDGET_S / (t_probe * todo)))
+    log(f'[bench] reference arm: {t_probe:.1f} s per pair at {SAMPLE_N_RAW} raw points x {todo} pairs exceeds '
+        f'{REF_TIME_BUDGET_S} s: sample reduced to {n_raw} raw points per scan')
+  t_small = t_probe
+  for i in range(1, max(args.warmup, 2 if n_raw != SAMPLE_N_RAW else 1)):
+    t_small, _ = cpu_sample_time(state, 100 + i, n_raw=n_raw)
+  # the per-pair cost has a floor (729 offsets x 21 layers of the 6-D network, however few voxels): if
+  # even the smallest sample cannot run K times inside the budget, fewer pairs are timed and the line
+  # says so (cpu_baseline.steps_executed); pairs/s is per executed pair either way
+  n_exec = args.steps if t_small * args.steps <= 1.5 * REF_TIME_BUDGET_S else \
+      max(3, int(REF_TIME_BUDGET_S / t_small))
   t0 = time.perf_counter()
   info = {}
-  for i in range(args.steps):
-    _, info = cpu_sample_time(state, i)
+  for i in range(n_exec):
+    _, info = cpu_sample_time(state, i, n_raw=n_raw)
   dt = time.perf_counter() - t0
-  val = args.steps / dt
+  val = n_exec / dt
   cfg = base_config(args.gpus)
   cfg['reference_arm'] = 'CPU oracle port on a bounded sample per step (MinkowskiEngine is not installable offline)'
   line = {'impl': 'reference', 'metric': 'scan_pairs_per_sec', 'value': val, 'unit': 'pairs/s',
           'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-          'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+          'ms_per_step': 1e3 * dt / n_exec, 'higher_is_better': True, 'scaling': 'weak',
           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
           'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
-                           'sample': sample_desc(info)},
+                           'sample': sample_desc(info, n_raw), 'steps_executed': n_exec},
           'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
   _emit(json.dumps(line))
 
