@@ -33,6 +33,14 @@ def dgr(state):
   return d
 
 
+@pytest.fixture(scope='module')
+def oracle_pair2(state):
+  """Oracle run of the pair two tests share (seed 2), once: with ICP; the pre-ICP pose is a tap."""
+  xyz0, xyz1, _ = syn.room_pair(2, n_raw=20000, extent=EXTENT)
+  T_icp, taps = op.register(state, xyz0, xyz1, use_icp=True)
+  return xyz0, xyz1, T_icp, taps
+
+
 def _rel(got, want):
   got, want = got.detach().cpu().double(), want.detach().cpu().double()
   return float(((got - want).abs() / (1 + want.abs())).max())
@@ -112,10 +120,10 @@ def test_register_known_answer_rigid_copy():
   assert T.dtype == np.float64 and T.shape == (4, 4)
 
 
-def test_register_end_to_end_vs_oracle(dgr, state):
-  xyz0, xyz1, _ = syn.room_pair(2, n_raw=20000, extent=EXTENT)
+def test_register_end_to_end_vs_oracle(dgr, state, oracle_pair2):
+  xyz0, xyz1, _, taps = oracle_pair2
   T = dgr.register(xyz0, xyz1)
-  T_o, taps = op.register(state, xyz0, xyz1)
+  T_o = taps.get('T_refined', np.eye(4))          # the oracle's pose before ICP (tap A)
   assert dgr.last_branch == taps['branch']
   assert abs(dgr.last_info['wsum'] - taps['wsum']) <= 1e-3 * max(1.0, taps['wsum'])
   if taps['branch'] == 'procrustes':
@@ -268,13 +276,12 @@ def test_icp_kernel_vs_oracle():
   assert te_f < te_i and re_f < re_i
 
 
-def test_register_with_icp_vs_oracle(state):
+def test_register_with_icp_vs_oracle(state, oracle_pair2):
   """Tap B: the literal return value of the reference's register() (use_icp = True)."""
   from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
   d = DeepGlobalRegistration(types.SimpleNamespace(weights=state, clip_weight_thresh=0.05, verbose=False))
-  xyz0, xyz1, _ = syn.room_pair(2, n_raw=20000, extent=EXTENT)
+  xyz0, xyz1, T_o, taps = oracle_pair2
   T = d.register(xyz0, xyz1)
-  T_o, taps = op.register(state, xyz0, xyz1, use_icp=True)
   assert d.last_branch == taps['branch'] == 'procrustes'
   te, re = syn.rte_rre(T, T_o)
   assert te <= 1e-3 and re <= 1e-3, (te, re, d.last_info, taps['icp'])
