@@ -40,8 +40,8 @@ WORKLOAD = '3dmatch_shape_pair_register'
 N_RAW = 250_000               # raw points per scan -> ~50k voxels at 0.05 m
 SAMPLE_N_RAW = 8_000          # CPU sample: same generator, ~4k voxels per cloud
 SAMPLE_EXTENT = (1.5, 1.2, 1.0)
-REF_TIME_BUDGET_S = 180       # --impl reference: W + K sample pairs must fit this
-REF_MIN_N_RAW = 1500          # ... but never fewer raw points than this per scan
+REF_TIME_BUDGET_S = 240       # --impl reference: stop starting full-size pairs once this is exceeded (>= 1 runs)
+REF_MIN_N_RAW = 1500          # the reference arm's untimed warm-up sample
 VOXEL = 0.05
 POOL = 3                      # distinct pairs per rank, cycled over the steps
 
@@ -54,6 +54,8 @@ def log(*a):
 
 
 def base_config(n_gpus):
+  """The SAME dict on both arms (the driver compares them): anything that differs between the arms
+  (voxel counts seen, sample notes) goes into other keys of the line."""
   return {'workload': WORKLOAD, 'n_raw_points_per_scan': N_RAW, 'voxel_size': VOXEL, 'feat_dim': 32,
           'fcgf_model': 'ResUNetBN2C(D=3,conv1_k=7)', 'inlier_model': 'ResUNetBN2C(D=6,conv1_k=3)',
           'conv_arithmetic': 'tcgen05 3xTF32 (fp32-accurate) + fp32 FFMA for conv1',
@@ -216,45 +218,64 @@ def sample_desc(info, n_raw=SAMPLE_N_RAW):
           "of MinkowskiEngine's CPU backend) + restated kNN / Procrustes / Adam refinement")
 
 
+def fixture_parity(T, key='T_refined'):
+  """TE [m] / RE [rad] of a pose of the bench's first pair (rank 0, seed 0, 250k raw points) against the CPU
+  oracle's pose stored in tests/golden/fullsize_config2.npz (tests/golden/make_golden_fullsize.py)."""
+  try:
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'fullsize_config2.npz'))
+    te, re = syn.rte_rre(np.asarray(T, np.float64).reshape(4, 4), g[key])
+    return {'te_m': te, 're_rad': re, 'tolerance': '1e-3 m / 1e-3 rad (north_star)', 'within_tolerance': bool(te <= 1e-3 and re <= 1e-3),
+            'against': 'CPU oracle pose before ICP of the same pair (BASELINE config 2: syn.room_pair(0, 250k raw points), '
+                       f'N0={int(g["n0"])}, N1={int(g["n1"])} voxels), fixture tests/golden/fullsize_config2.npz',
+            'config': WORKLOAD}
+  except Exception as e:   # noqa: BLE001
+    return {'te_m': None, 're_rad': None, 'error': repr(e)}
+
+
 def run_reference(args):
+  """The reference's CPU implementation of the path (the oracle port: MinkowskiEngine is not installable
+  offline, nothing of the reference compiles into oracle/_ref) on the SAME configuration as the B200 arm:
+  full-size pairs of the same generator and seeds.  One such pair is minutes of CPU, so the run executes as
+  many of the K steps as fit REF_TIME_BUDGET_S after the first (at least one) and says how many
+  (cpu_baseline.steps_executed); pairs/s is per executed full-size pair, nothing is extrapolated."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
+  from oracle import pipeline as op
   state = syn.make_checkpoint(0)
   cores = cpu_threads()
   log(f'[bench] reference arm: {cores} threads (nproc {os.cpu_count()}, usable {effective_cpus()})')
-  # the whole run (W warm-up + K timed sample pairs) has to end within a few minutes whatever K is:
-  # the first warm-up pair is the probe; if K + W pairs of that size would not fit the budget, the
-  # sample shrinks (time is ~linear in the number of voxels) - the actual sample is reported
-  n_raw = SAMPLE_N_RAW
-  t_probe, _ = cpu_sample_time(state, 100)
-  todo = args.steps + max(args.warmup - 1, 0)
-  if t_probe * todo > REF_TIME_BUDGET_S:
-    n_raw = max(REF_MIN_N_RAW, int(SAMPLE_N_RAW * REF_TIME_BUDGET_S / (t_probe * todo)))
-    log(f'[bench] reference arm: {t_probe:.1f} s per pair at {SAMPLE_N_RAW} raw points x {todo} pairs exceeds '
-        f'{REF_TIME_BUDGET_S} s: sample reduced to {n_raw} raw points per scan')
-  t_small = t_probe
-  for i in range(1, max(args.warmup, 2 if n_raw != SAMPLE_N_RAW else 1)):
-    t_small, _ = cpu_sample_time(state, 100 + i, n_raw=n_raw)
-  # the per-pair cost has a floor (729 offsets x 21 layers of the 6-D network, however few voxels): if
-  # even the smallest sample cannot run K times inside the budget, fewer pairs are timed and the line
-  # says so (cpu_baseline.steps_executed); pairs/s is per executed pair either way
-  n_exec = args.steps if t_small * args.steps <= 1.5 * REF_TIME_BUDGET_S else \
-      max(3, int(REF_TIME_BUDGET_S / t_small))
-  t0 = time.perf_counter()
-  info = {}
-  for i in range(n_exec):
-    _, info = cpu_sample_time(state, i, n_raw=n_raw)
-  dt = time.perf_counter() - t0
+  # warm-up: thread pools / allocator on a tiny sample of the same generator (seconds), untimed
+  t_warm, _ = cpu_sample_time(state, 100, n_raw=REF_MIN_N_RAW)
+  log(f'[bench] reference arm: warm-up sample {t_warm:.1f} s; timing full-size pairs')
+  times, info, parity = [], {}, None
+  t_begin = time.perf_counter()
+  for i in range(args.steps):
+    xyz0, xyz1, _ = syn.room_pair(1000 * rank + (i % POOL), n_raw=N_RAW)
+    t = time.perf_counter()
+    T, taps = op.register(state, xyz0, xyz1)
+    times.append(time.perf_counter() - t)
+    info = {'n0': int(len(taps['coords0'])), 'n1': int(len(taps['coords1'])), 'branch': taps['branch']}
+    if i == 0:
+      parity = fixture_parity(T)
+    log(f'[bench] reference arm: pair {i} N0={info["n0"]} N1={info["n1"]} {times[-1]:.1f} s')
+    if time.perf_counter() - t_begin + times[-1] > REF_TIME_BUDGET_S:
+      break
+  n_exec = len(times)
+  dt = float(sum(times))
   val = n_exec / dt
-  cfg = base_config(args.gpus)
-  cfg['reference_arm'] = 'CPU oracle port on a bounded sample per step (MinkowskiEngine is not installable offline)'
   line = {'impl': 'reference', 'metric': 'scan_pairs_per_sec', 'value': val, 'unit': 'pairs/s',
           'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
           'ms_per_step': 1e3 * dt / n_exec, 'higher_is_better': True, 'scaling': 'weak',
-          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': base_config(args.gpus),
           'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
-                           'sample': sample_desc(info, n_raw), 'steps_executed': n_exec},
+                           'sample': f'{n_exec} FULL-SIZE pair(s) of the workload (same generator and seeds as the B200 arm: '
+                                     f'{N_RAW} raw points per scan -> N0={info["n0"]}, N1={info["n1"]} voxels), not a reduced sample; '
+                                     'CPU path = oracle port (torch-CPU index_select/mm/index_add per kernel offset, the algorithm '
+                                     "of MinkowskiEngine's CPU backend) + restated kNN / Procrustes / Adam refinement",
+                           'steps_executed': n_exec, 'seconds_per_pair': times,
+                           'warmup_executed': f'1 pair of {REF_MIN_N_RAW} raw points ({t_warm:.1f} s)'},
+          'workload_detail': info, 'parity': parity,
           'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
   _emit(json.dumps(line))
 
@@ -424,10 +445,21 @@ def run_ours(args):
   cpu_s, info = cpu_sample_time(state, 0, reps=1)
   cpu = {'value': 1.0 / cpu_s, 'unit': 'pairs/s', 'cores': cpu_threads(), 'kind': 'port',
          'sample': sample_desc(info), 'seconds_per_sample_pair': cpu_s}
+  try:     # the same-config CPU time: one FULL-SIZE oracle run of this arm's first pair, recorded with the fixture
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'fullsize_config2.npz'))
+    sec = json.loads(str(g['seconds']))
+    cpu['full_size_pair'] = {'seconds_through_refine': sec['total_through_refine'], 'threads': sec['threads'],
+                             'pairs_per_sec': 1.0 / sec['total_through_refine'],
+                             'where': 'build container, recorded by tests/golden/make_golden_fullsize.py; '
+                                      '`bench.py --impl reference` times the same full-size pair on this box'}
+  except Exception:   # noqa: BLE001
+    pass
 
+  # pose of this arm's first pair (timed `value` loop, step 0) against the CPU oracle's pose of the same pair
+  parity = fixture_parity(res['poses'][0][:16].numpy()) if rank == 0 else None
+  detail = dict(n0=dgr.last_info.get('n0'), n1=dgr.last_info.get('n1'), branch=dgr.last_branch,
+                refine_iterations=dgr.last_info.get('iterations'))
   cfg_out = base_config(world)
-  cfg_out.update(n0=dgr.last_info.get('n0'), n1=dgr.last_info.get('n1'), branch=dgr.last_branch,
-                 refine_iterations=dgr.last_info.get('iterations'))
   h2d = int(sum(a.nbytes + b.nbytes for a, b, _ in pairs_host) / POOL)
   fixed_d2h = 2 * 8 + 8 + 9 * 4 + 8 + 64     # counts, spec flags, coarse-map sizes, wsum, pose
   line = {'metric': 'scan_pairs_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K,
@@ -438,7 +470,7 @@ def run_ours(args):
                   'ms_per_step': res_e2e['ms'] / K, 'wall_ms_per_step': 1e3 * res_e2e['wall'] / K},
           'gpu_launches': int(res['launches']), 'gpu_launches_per_step': res['launches'] / K,
           'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor,
-          'kernel_share_of_step': kernel_share, 'cpu_baseline': cpu,
+          'kernel_share_of_step': kernel_share, 'cpu_baseline': cpu, 'parity': parity, 'workload_detail': detail,
           'wall_ms_per_step': 1e3 * res['wall'] / K,
           'host_cgroup_throttled_ms_during_timing': (thr1 - thr0) if thr0 is not None and thr1 is not None else None,
           'cuda_allocator_events_during_timing': alloc_delta,

@@ -137,11 +137,13 @@ def read_pair_list(path):
   return pairs
 
 
-def evaluate(method, pairs, rte_thresh=0.3, rre_thresh=15.0, log=None):
-  """Register every pair (this rank's share; results gathered on all ranks).
+def evaluate(method, pairs, rte_thresh=0.3, rre_thresh=15.0, log=None, device=None):
+  """Register every pair (this rank's share; results gathered on all ranks).  `device`: where the
+  gather buffer lives - a CUDA device under an NCCL process group (NCCL has no CPU backend), None for
+  gloo / a single process.
   -> dict(stats [n, 5], poses [n, 4, 4], branch [n], groups [names])."""
   groups = sorted({p.group for p in pairs})
-  rows = sharding.register_pairs(method, [(p.file0, p.file1) for p in pairs]).numpy().astype(np.float64)
+  rows = sharding.register_pairs(method, [(p.file0, p.file1) for p in pairs], device=device).numpy().astype(np.float64)
   n = len(pairs)
   stats = np.zeros((n, 5))
   poses = rows[:, :16].reshape(n, 4, 4)
@@ -214,12 +216,23 @@ def main(argv=None):
     pairs = kitti_pairs(args.kitti_dir)
   else:
     pairs = read_pair_list(args.pair_list)
-  result = evaluate(dgr, pairs, args.success_rte_thresh, args.success_rre_thresh,
-                    log=print if rank == 0 else None)
+  # the output directory is settled BEFORE hours of registration: created if missing; when that is
+  # impossible fall back to the current directory as the reference does (scripts/test_3dmatch.py:135-137)
+  out_dir = args.out_dir
   if rank == 0:
-    out = os.path.join(args.out_dir, 'dgr-b200-stats.npz')
+    try:
+      os.makedirs(out_dir, exist_ok=True)
+    except OSError as e:
+      print(f'cannot create {out_dir!r} ({e}); saving to the current directory')
+      out_dir = '.'
+  result = evaluate(dgr, pairs, args.success_rte_thresh, args.success_rre_thresh,
+                    log=print if rank == 0 else None, device=torch.device('cuda', local))
+  if rank == 0:
+    summary = summarize(result)
+    print(json.dumps(dict(summary, world_size=world)))          # the summary first: a failing save loses nothing
+    out = os.path.join(out_dir, 'dgr-b200-stats.npz')
     np.savez(out, stats=result['stats'][None], names=['DGR'], poses=result['poses'], groups=result['groups'])
-    print(json.dumps(dict(summarize(result), world_size=world, saved=out)))
+    print(json.dumps(dict(saved=out)))
   if world > 1:
     dist.destroy_process_group()
 

@@ -28,9 +28,10 @@ _PLY_TYPES = {
 class PointCloud:
   """Points [N, 3] float64 plus optional per-point attributes read alongside them."""
 
-  def __init__(self, points=None, **attributes):
+  def __init__(self, points=None, attributes=None, **more_attributes):
     self.points = np.zeros((0, 3)) if points is None else points
-    self.attributes = attributes
+    # per-point extras as ONE dict (a PLY property may be called anything, 'points' included)
+    self.attributes = dict(attributes or {}, **more_attributes)
     self.normals = None
 
   @property
@@ -145,7 +146,7 @@ def read_ply(path):
         rec = np.frombuffer(buf, dtype=dt)
         cols = {n: rec[n] for n in names}
       pts = np.stack([np.asarray(cols[a], dtype=np.float64) for a in 'xyz'], axis=1)
-      extra = {n: np.asarray(v) for n, v in cols.items() if n not in 'xyz'}
+      extra = {n: np.asarray(v) for n, v in cols.items() if n not in ('x', 'y', 'z')}
       return pts, extra
   raise ValueError('PLY file has no vertex element')
 
@@ -217,7 +218,7 @@ def read_point_cloud(path):
   what open3d holds and why the reference voxelises PLY input in float64)."""
   if os.path.splitext(path)[1].lower() == '.ply':
     pts, extra = read_ply(path)
-    return PointCloud(pts, **extra)
+    return PointCloud(pts, attributes=extra)
   return PointCloud(read_points(path))
 
 

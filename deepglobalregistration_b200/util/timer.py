@@ -21,12 +21,23 @@ class RunningStat:
     self.count, self.avg, self._m2, self.sum, self.val = 0, 0.0, 0.0, 0.0, 0.0
 
   def update(self, value, n=1):
+    # arrays / tensors as the reference's AverageMeter takes them (util/timer.py:25-37): the sample is
+    # the mean, its multiplicity the element count
+    size = getattr(value, 'size', None)
+    if callable(size):            # torch.Tensor
+      n, value = int(value.numel()), float(value.float().mean()) if value.numel() else 0.0
+    elif size is not None and not isinstance(value, (int, float)):   # numpy array / scalar
+      import numpy as np
+      arr = np.asarray(value, dtype=np.float64)
+      n, value = (int(arr.size), float(arr.mean())) if arr.ndim else (n, float(arr))
     value = float(value)
-    for _ in range(int(n)):
-      self.count += 1
+    n = int(n)
+    if n > 0:                     # n equal samples merged in one step (Chan et al. pairwise update)
+      total = self.count + n
       delta = value - self.avg
-      self.avg += delta / self.count
-      self._m2 += delta * (value - self.avg)
+      self.avg += delta * n / total
+      self._m2 += delta * delta * self.count * n / total
+      self.count = total
     self.sum += value * n
     self.val = value
 
@@ -55,6 +66,14 @@ class Timer(RunningStat):
 
   def tic(self):
     self._t0 = self._now()
+
+  @property
+  def start_time(self):          # attribute names of the reference's Timer (util/timer.py:40-54)
+    return self._t0
+
+  @property
+  def sq_sum(self):
+    return self._m2 + self.count * self.avg * self.avg
 
   def toc(self, average=True):
     if self._t0 is None:

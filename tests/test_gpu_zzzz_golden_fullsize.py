@@ -1,0 +1,150 @@
+"""CUDA path vs the CPU oracle AT THE BASELINE.json SIZES, through committed fixtures
+(tests/golden/fullsize_config{2,3}.npz, made by tests/golden/make_golden_fullsize.py: one oracle run
+of the bench's own seed-0 pair - 250k raw points, ~51k / ~40k voxels - and of the full KITTI-shape
+pair syn.lidar_pair(0)).  /root/reference and the minutes-long oracle run are not needed here.
+
+Bars (north_star): voxel selection / coordinates / 6-D coordinates bit-exact (sha256 of the arrays);
+features <= 5e-5; correspondences identical wherever the float64 top-2 gap exceeds the feature
+tolerance, and - on the GPU's own features - identical to a float64 brute force outside the 1e-6
+ambiguity band; inlier logits <= 5e-5 relative and weights <= 5e-5 on the ORACLE's correspondences;
+pose after Procrustes + refinement and after ICP within 1e-3 rad / 1e-3 m, stage-isolated (oracle
+weights in) and free-running (register() end to end)."""
+import hashlib
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from deepglobalregistration_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+FEAT_TOL = 5e-5
+GAP_SAFE = 2e-3        # relative top-2 gap above which a 5e-5 feature perturbation cannot flip the arg-min
+
+
+def sha(a):
+  return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _case(config):
+  if config == 2:
+    return syn.make_checkpoint(0), syn.room_pair(0, n_raw=250_000)
+  return syn.make_checkpoint(3, voxel_size=0.3, feat_conv1_kernel_size=5), syn.lidar_pair(0)
+
+
+@pytest.fixture(scope='module', params=[3, 2], ids=['config3_kitti_shape', 'config2_3dmatch_shape'])
+def run(request):
+  """One pass through the stages on the GPU, shared by the tests of a configuration."""
+  from deepglobalregistration_b200 import _abi
+  from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
+  config = request.param
+  gold = np.load(os.path.join(GOLD, f'fullsize_config{config}.npz'))
+  state, (xyz0, xyz1, _) = _case(config)
+  d = DeepGlobalRegistration(types.SimpleNamespace(weights=state, clip_weight_thresh=0.05, verbose=False))
+  r = types.SimpleNamespace(config=config, gold=gold, d=d, abi=_abi, xyz0=xyz0, xyz1=xyz1)
+  with torch.no_grad():
+    r.p0, r.c0, _ = d.preprocess(xyz0, 0, _batch=0)
+    r.sel0 = d._last_sel.cpu().numpy().astype(np.int64)
+    r.p1, r.c1, _ = d.preprocess(xyz1, 1, _batch=1)
+    r.sel1 = d._last_sel.cpu().numpy().astype(np.int64)
+    r.F0, r.F1 = d.fcgf_feature_extraction_pair(r.c0, r.c1)
+    r.idx1 = _abi.knn_top1(r.F0, r.F1)
+  return r
+
+
+def test_voxelisation_bit_exact(run):
+  g = run.gold
+  assert len(run.c0) == int(g['n0']) and len(run.c1) == int(g['n1'])
+  assert sha(run.sel0) == str(g['sha_sel0']) and sha(run.sel1) == str(g['sha_sel1'])
+  c1 = run.c1.cpu().numpy().copy()
+  assert np.all(c1[:, 0] == 1)
+  c1[:, 0] = 0            # the oracle voxelises each cloud on its own (batch 0); the pair batches 0 / 1
+  assert sha(run.c0.cpu().numpy()) == str(g['sha_coords0']) and sha(c1) == str(g['sha_coords1'])
+
+
+def test_fcgf_features(run):
+  g = run.gold
+  step = int(g['feat_step'])
+  for F, want in ((run.F0, g['feat0_rows']), (run.F1, g['feat1_rows'])):
+    got = F[::step].cpu().numpy()
+    assert got.shape == want.shape
+    err = float(np.abs(got.astype(np.float64) - want).max())
+    assert err <= FEAT_TOL, err
+
+
+def test_correspondences(run):
+  """(a) vs the oracle's arg-min wherever its float64 top-2 gap is safely above the feature tolerance;
+  (b) vs a float64 brute force over the GPU's OWN features outside the 1e-6 ambiguity band (the
+  oracle's criterion, oracle/registration.py::feature_knn) - every row of the full-size problem."""
+  g = run.gold
+  idx = run.idx1.cpu().numpy()
+  want, gap = g['idx1'], g['knn_gap']
+  safe = gap > GAP_SAFE
+  assert safe.mean() > 0.5
+  bad = int((idx[safe] != want[safe]).sum())
+  assert bad == 0, f'{bad} of {int(safe.sum())} unambiguous correspondences differ from the oracle'
+  flips = int((idx != want).sum())
+  print(f'config {run.config}: {flips} of {len(idx)} correspondences differ, all inside the gap <= {GAP_SAFE} band '
+        f'({int((~safe).sum())} rows)')
+  A, B = run.F0.double(), run.F1.double()
+  bn = (B * B).sum(1)
+  for s in range(0, len(A), 4096):
+    a = A[s:s + 4096]
+    d2 = ((a * a).sum(1, keepdim=True) + bn[None] - 2.0 * (a @ B.t())).clamp_min(0)
+    top = torch.topk(d2, 2, dim=1, largest=False)
+    amb = (top.values[:, 1] - top.values[:, 0]) <= 1e-6 * (top.values[:, 1] + 1e-7)
+    ok = (top.indices[:, 0] == run.idx1[s:s + 4096].long()) | amb
+    assert bool(ok.all()), f'{int((~ok).sum())} rows of chunk {s} differ from the float64 brute force'
+
+
+def test_inlier_network_and_registration_on_oracle_correspondences(run):
+  g, abi, d = run.gold, run.abi, run.d
+  with torch.no_grad():
+    idx1 = torch.from_numpy(g['idx1']).int().cuda()
+    c6 = abi.inlier_coords(run.c0, run.c1, idx1)
+    assert sha(c6.cpu().numpy()) == str(g['sha_coords6'])
+    from deepglobalregistration_b200.me.coords import CoordinateManager
+    c6._dgr_manager = CoordinateManager(c6, assume_unique=True)
+    logit = d.inlier_prediction(torch.ones(len(idx1), 1, device='cuda'), c6).reshape(-1)
+    want = torch.from_numpy(g['logit']).cuda()
+    rel = float(((logit - want).abs() / (1 + want.abs())).max())
+    assert rel <= 5e-5, rel
+    w, wsum = abi.sigmoid_clip_sum(logit.contiguous(), 0.05)
+    w_o, wsum_o = abi.sigmoid_clip_sum(want.contiguous(), 0.05)
+    # weights: <= 5e-5 except where a logit sits within the tolerance of the clip threshold
+    near_clip = (torch.sigmoid(want) - 0.05).abs() <= 1e-4
+    assert float(((w - w_o).abs() * (~near_clip)).max()) <= 5e-5
+    assert abs(float(wsum) - float(g['wsum'])) <= 1e-3 * float(g['wsum']) + 0.1 * int(near_clip.sum())
+    assert str(g['branch']) == 'procrustes'
+    # Procrustes + SE(3) refinement on the oracle's weights
+    res = abi.se3_register(run.p0, run.p1, w_o.reshape(-1).contiguous(), idx1=idx1,
+                           quantization_size=2 * d.voxel_size, break_threshold_ratio=1e-4).cpu().numpy()
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = res[:9].reshape(3, 3), res[9:12]
+    te, re = syn.rte_rre(T, g['T_refined'])
+    print(f'config {run.config}: refinement on oracle weights TE={te:.2e} RE={re:.2e} '
+          f'iterations {int(res[12])} (oracle {int(g["refine_iters"])})')
+    assert te <= 1e-3 and re <= 1e-3, (te, re)
+    # ICP from the oracle's refined pose
+    icp = abi.icp_point_to_point(run.p0, run.p1, run.c1._dgr_manager, d.voxel_size, 2 * d.voxel_size,
+                                 g['T_refined'], batch=1).cpu().numpy()
+    te, re = syn.rte_rre(icp[:16].reshape(4, 4), g['T_icp'])
+    assert te <= 1e-3 and re <= 1e-3, (te, re)
+    assert abs(icp[16] - float(g['icp_fitness'])) <= 1e-3 and abs(icp[17] - float(g['icp_rmse'])) <= 1e-4
+
+
+def test_register_end_to_end(run):
+  """The literal register() (free-running: its own correspondences and weights) against the oracle's
+  pose before and after ICP."""
+  g, d = run.gold, run.d
+  for use_icp, key in ((False, 'T_refined'), (True, 'T_icp')):
+    d.use_icp = use_icp
+    T = d.register(run.xyz0, run.xyz1)
+    assert d.last_branch == 'procrustes'
+    assert abs(d.last_info['wsum'] - float(g['wsum'])) <= 2e-3 * float(g['wsum'])
+    te, re = syn.rte_rre(T, g[key])
+    print(f'config {run.config}: register(use_icp={use_icp}) vs oracle TE={te:.2e} m RE={re:.2e} rad')
+    assert te <= 1e-3 and re <= 1e-3, (use_icp, te, re, d.last_info)
