@@ -44,6 +44,7 @@ REF_TIME_BUDGET_S = 240       # --impl reference: stop starting full-size pairs 
 REF_MIN_N_RAW = 1500          # the reference arm's untimed warm-up sample
 VOXEL = 0.05
 POOL = 3                      # distinct pairs per rank, cycled over the steps
+INFLIGHT = int(os.environ.get('DGR_BENCH_INFLIGHT', '2'))   # pairs in flight per GPU (SURVEY 8e allows two)
 
 
 _emit = print
@@ -184,6 +185,25 @@ def effective_cpus():
   return n
 
 
+def pin_rank_to_numa_node(local_rank):
+  """Keep this rank's host threads on the CPU cores local to its GPU (the box has two sockets: GPUs 0-3 hang
+  off one, 4-7 off the other); a rank whose launch threads sit on the far socket pays a cross-socket hop on
+  every launch and host read.  Best effort: silently does nothing when the topology cannot be read."""
+  try:
+    p = torch.cuda.get_device_properties(local_rank)
+    path = f'/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/local_cpulist'
+    cpus = set()
+    for part in open(path).read().strip().split(','):
+      lo, _, hi = part.partition('-')
+      cpus.update(range(int(lo), int(hi or lo) + 1))
+    cpus &= os.sched_getaffinity(0)
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+      log(f'[bench] local rank {local_rank}: pinned to {len(cpus)} cores local to the GPU ({min(cpus)}-{max(cpus)})')
+  except Exception as e:   # noqa: BLE001
+    log(f'[bench] NUMA pinning skipped: {e!r}')
+
+
 CPU_THREADS = None
 
 
@@ -230,6 +250,39 @@ def fixture_parity(T, key='T_refined'):
             'config': WORKLOAD}
   except Exception as e:   # noqa: BLE001
     return {'te_m': None, 're_rad': None, 'error': repr(e)}
+
+
+def stage_isolated_parity(dgr, pair_dev):
+  """The last stage at the bench's size on the ORACLE's inputs: register the pair once more, take the voxelised
+  points from the executor, and run Procrustes + refinement on the oracle's correspondences and weights (fixture).
+  End-to-end poses of a random-init network are ill-conditioned (its correspondences are unrelated points; a
+  handful of arg-min flips inside the features' rounding noise move the optimum by centimetres), so this is the
+  number that isolates the arithmetic; the earlier stages are pinned the same way in
+  tests/test_gpu_zzzz_golden_fullsize.py."""
+  try:
+    from deepglobalregistration_b200 import _abi
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'fullsize_config2.npz'))
+    dgr.register(*pair_dev)
+    ctx = dgr._last_ctx
+    n0 = dgr.last_info['n0']
+    if n0 != int(g['n0']) or dgr.last_info['n1'] != int(g['n1']):
+      return {'error': f'voxel counts differ from the fixture: {n0}, {dgr.last_info["n1"]}'}
+    xyz = ctx.tap('xyz')
+    idx_gpu = ctx.tap('idx1').cpu().numpy()
+    flips = int((idx_gpu != g['idx1']).sum())
+    _abi.refresh_stream()
+    dev = xyz.device
+    w, _ = _abi.sigmoid_clip_sum(torch.from_numpy(g['logit']).to(dev).contiguous(), 0.05)
+    res = _abi.se3_register(xyz[:n0].contiguous(), xyz[n0:].contiguous(), w.reshape(-1).contiguous(),
+                            idx1=torch.from_numpy(g['idx1']).to(dev).int().contiguous(),
+                            quantization_size=2 * dgr.voxel_size, break_threshold_ratio=1e-4).cpu().numpy()
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = res[:9].reshape(3, 3), res[9:12]
+    te, re = syn.rte_rre(T, g['T_refined'])
+    return {'te_m': te, 're_rad': re, 'within_tolerance': bool(te <= 1e-3 and re <= 1e-3),
+            'correspondences_differing_from_oracle_end_to_end': flips, 'correspondences': int(n0)}
+  except Exception as e:   # noqa: BLE001
+    return {'error': repr(e)}
 
 
 def run_reference(args):
@@ -295,14 +348,26 @@ def run_ours(args):
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
+  pin_rank_to_numa_node(local)
 
   state = syn.make_checkpoint(0)
   cfg = types.SimpleNamespace(weights=state, clip_weight_thresh=0.05, verbose=False)
   dgr = DeepGlobalRegistration(cfg, device=dev)
   dgr.use_icp = False     # the benchmarked unit is tap A (through the refinement), as on the CPU arm
+  inflight = INFLIGHT if dgr._native_ok() else 1
 
-  # this rank's pairs (seeds disjoint across ranks): host copies for e2e, device copies for `value`
-  pairs_host = [syn.room_pair(1000 * rank + i, n_raw=N_RAW) for i in range(POOL)]
+  strong = args.pairs > 0
+  if strong:
+    # BASELINE config 4: a fixed set of pairs (seeds 0 .. pairs-1) round-robin over the ranks, same total at every N
+    seeds = sharding.shard_indices(args.pairs, rank, world)
+    n_steps_default = len(seeds)
+  else:
+    # this rank's pairs (seeds disjoint across ranks), cycled over the steps: weak scaling
+    seeds = [1000 * rank + i for i in range(POOL)]
+    n_steps_default = args.steps
+  pool = min(len(seeds), POOL) if not strong else len(seeds)
+  log(f'[bench] rank {rank}/{world}: generating {pool} pair(s)')
+  pairs_host = [syn.room_pair(sd, n_raw=N_RAW) for sd in seeds[:pool]]
   pairs_dev = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b, _ in pairs_host]
 
   def barrier():
@@ -310,82 +375,101 @@ def run_ours(args):
       dist.barrier()
     torch.cuda.synchronize()
 
-  def gather_poses(rows):
+  def gather_poses(rows, total):
     # the path's only collective: one all-gather of [pairs, 20] results (NCCL over NVLink)
-    return sharding.gather_results(rows, world * len(rows), device=dev)
+    return sharding.gather_results(rows, total, device=dev)
 
-  def timed(n_steps, host_inputs, profile=False):
-    """K steps bracketed by barrier + synchronize; device time by CUDA events."""
+  def timed(n_steps, host_inputs):
+    """n_steps register() calls (`inflight` pairs in flight) bracketed by barrier + synchronize; device time by
+    CUDA events; the result gather is inside the timed region."""
     barrier()
-    if profile:
-      _abi.CONV_PROFILE = []
-    l0, d0 = _abi.lib().dgr_launch_count(), _abi.D2H_BYTES
+    src = pairs_host if host_inputs else pairs_dev
+    pairs = [src[s % pool][:2] for s in range(n_steps)]
+    l0 = _abi.lib().dgr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     e0.record()
-    poses, marks = [], []
-    for s in range(n_steps):
-      a, b = (pairs_host[s % POOL][:2] if host_inputs else pairs_dev[s % POOL])
-      T = dgr.register(a, b)
-      poses.append(sharding.pack_result(T, dgr.last_info.get('wsum', 0.0), dgr.last_info.get('iterations', 0),
-                                        dgr.last_branch))
-      ev = torch.cuda.Event(enable_timing=True)
-      ev.record()
-      marks.append(ev)
-    gathered = gather_poses(poses)
+    out = dgr.register_batch(pairs, inflight=inflight)
+    rows = [sharding.pack_result(T, info.get('wsum', 0.0), info.get('iterations', 0), branch) for T, branch, info in out]
+    if strong:
+      gathered = gather_poses(rows, args.pairs)
+    else:
+      gathered = gather_poses(rows, world * len(rows))
     e1.record()
     barrier()
     wall = time.perf_counter() - w0
-    ms = e0.elapsed_time(e1)
-    prof, _abi.CONV_PROFILE = _abi.CONV_PROFILE, None
+    ms_local = ms = e0.elapsed_time(e1)
     launches = _abi.lib().dgr_launch_count() - l0
-    d2h = _abi.D2H_BYTES - d0
+    d2h = sum(info.get('d2h_bytes', 0) for _, _, info in out)
+    reads = sum(info.get('host_reads', 0) for _, _, info in out)
+    per_rank = None
     if world > 1:
       tm = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
-      dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-      ms, wall = float(tm[0]), float(tm[1]) / 1e3
-    steps_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
-    return dict(ms=ms, wall=wall, launches=launches, d2h=d2h, prof=prof, poses=gathered, steps_ms=steps_ms)
+      allt = [torch.empty_like(tm) for _ in range(world)]
+      dist.all_gather(allt, tm)
+      per_rank = [float(t[0]) for t in allt]
+      ms, wall = max(per_rank), max(float(t[1]) for t in allt) / 1e3
+    done = sorted(info.get('t_done', w0) for _, _, info in out)
+    steps_ms = [1e3 * d for d in np.diff([w0] + done)]
+    return dict(ms=ms, ms_local=ms_local, wall=wall, launches=launches, d2h=d2h, reads=reads, poses=gathered,
+                steps_ms=steps_ms, per_rank_ms=per_rank, last=out[-1])
 
-  # started before the warm-up: nvidia-smi's own start-up (NVML init) must not land in the timed region
+  def profiled_serial_pass(n_steps):
+    """One pair at a time with per-launch CUDA events around every convolution launch (the roofline of the
+    dominant kernel); with two pairs in flight the events would time two kernels sharing the GPU."""
+    ctx = dgr.native_context(0)
+    torch.cuda.synchronize()
+    ctx.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stages = {}
+    for s in range(n_steps):
+      dgr.register(*pairs_dev[s % pool])
+      for k, v in ctx.stage_times().items():
+        stages.setdefault(k, []).append(v)
+    e1.record()
+    torch.cuda.synchronize()
+    rows = ctx.profile_read(64 * n_steps + 64)
+    ctx.profile(False)
+    return rows, e0.elapsed_time(e1), {k: float(np.mean(v)) for k, v in stages.items()}
+
+  # started before the warm-up: the sampler's own start-up (NVML init) must not land in the timed region
   sampler = ClockSampler(local) if rank == 0 and not os.environ.get('DGR_BENCH_NO_SAMPLER') else None
-  log(f'[bench] rank {rank}/{world}: model + {POOL} pairs ready, warming up')
-  # warm-up: every pair of the pool at least max(W, 3) times on both input paths, so that the
-  # caching allocator has seen every buffer size before anything is timed
-  n_warm = max(args.warmup, 3) * POOL
+  K = n_steps_default
+  log(f'[bench] rank {rank}/{world}: model + {pool} pairs ready ({inflight} in flight), warming up')
+  # warm-up: every pair of the pool at least max(W, 3) times on both input paths (arena growth, pinned staging,
+  # NCCL channels), then one untimed rehearsal of exactly the timed loops
+  n_warm = max(args.warmup, 3) * min(pool, POOL)
   timed(n_warm, host_inputs=False)
-  timed(POOL, host_inputs=True)
-  # one untimed rehearsal of exactly the timed loops: flushes every lazy initialisation
-  # (allocator size classes, NCCL channels, pinned staging) out of the measurement
-  timed(args.steps, host_inputs=False)
-  timed(args.steps, host_inputs=True)
+  timed(max(min(pool, POOL), 2), host_inputs=True)
+  timed(K, host_inputs=False)
+  timed(K, host_inputs=True)
   gc.collect()
   log('[bench] warm-up done, timing')
 
   t_start = time.time()
   thr0 = cgroup_throttled_ms()
-  ms0 = torch.cuda.memory_stats(dev)
-  res = timed(args.steps, host_inputs=False, profile=True)     # `value`: scans resident in HBM
-  t_mid = time.time()
-  res_e2e = timed(args.steps, host_inputs=True)                 # `e2e`: host buffers in, pose out
+  res = timed(K, host_inputs=False)               # `value`: scans resident in HBM
+  res_e2e = timed(K, host_inputs=True)            # `e2e`: host buffers in, pose out
   t_end = time.time()
   thr1 = cgroup_throttled_ms()
-  ms1 = torch.cuda.memory_stats(dev)
-  alloc_delta = {k: int(ms1.get(k, 0) - ms0.get(k, 0)) for k in ('num_device_alloc', 'num_device_free',
-                                                                  'num_alloc_retries', 'num_sync_all_streams')}
   clocks = sampler.stop(t_start, t_end) if sampler else None
+  arena = [dgr.native_context(k).stats() for k in range(inflight)] if dgr._native_ok() else None
+
+  prof_rows, serial_ms, stage_ms, n_prof = None, None, None, min(K, 20)
+  if rank == 0 and dgr._native_ok():
+    prof_rows, serial_ms, stage_ms = profiled_serial_pass(n_prof)
 
   # supplementary: the literal reference call (use_icp = True, host arrays in, pose out).  Single-rank
   # only (a failure here must not strand peers in a collective) and never fatal to the contract line.
   e2e_icp = None
-  if world == 1:
+  if world == 1 and not strong:
     try:
       dgr.use_icp = True
-      timed(2 * POOL, host_inputs=True)
-      r_icp = timed(args.steps, host_inputs=True)
-      e2e_icp = {'value': args.steps / (r_icp['ms'] / 1e3), 'unit': 'pairs/s', 'ms_per_step': r_icp['ms'] / args.steps,
-                 'step_ms_median': float(np.median(r_icp['steps_ms'])),
-                 'icp_iterations_last_pair': dgr.last_info.get('icp_iterations'),
+      timed(2 * pool, host_inputs=True)
+      r_icp = timed(K, host_inputs=True)
+      e2e_icp = {'value': K / (r_icp['ms'] / 1e3), 'unit': 'pairs/s', 'ms_per_step': r_icp['ms'] / K,
+                 'icp_iterations_last_pair': r_icp['last'][2].get('icp_iterations'),
                  'note': 'register() exactly as the reference defaults it: Procrustes + refinement + '
                          'point-to-point ICP; outside the contract value, which is SURVEY 8(d)\'s unit'}
     except Exception as e:   # noqa: BLE001
@@ -398,11 +482,11 @@ def run_ours(args):
       dist.destroy_process_group()
     return
 
-  K = args.steps
-  value = world * K / (res['ms'] / 1e3)
-  e2e = world * K / (res_e2e['ms'] / 1e3)
+  n_total = args.pairs if strong else world * K
+  value = n_total / (res['ms'] / 1e3)
+  e2e = n_total / (res_e2e['ms'] / 1e3)
 
-  # ---- roofline of the dominant kernel (live CUDA events around every launch) ---------------
+  # ---- roofline of the dominant kernel (live CUDA events around every launch, serial pass) ------------
   peaks, peak_src = None, 'fallback (B200_PROFILING.md: 6650 GB/s, 1590 TFLOP/s bf16)'
   try:
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -411,34 +495,41 @@ def run_ours(args):
     pass
   hbm_peak = float(peaks['hbm_gbs']) if peaks else 6650.0
   bf16_peak = float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])) if peaks else 1400.0
-  by = {}
-  for name, a, b, flops, nbytes in res['prof']:
-    d = by.setdefault(name, [0, 0.0, 0.0, 0.0])
-    d[0] += 1
-    d[1] += a.elapsed_time(b)
-    d[2] += flops
-    d[3] += nbytes
-  dom = max(by, key=lambda k: by[k][1]) if by else None
   roofline, roofline_tensor, kernel_share = None, None, None
-  if dom:
+  if prof_rows is not None and len(prof_rows):
+    names = {0: 'spconv_tc_kernel', 1: 'spconv_fwd_kernel', 2: 'spconv_table_kernel'}
+    by = {}
+    for ms, flops, nbytes, kind in prof_rows:
+      d = by.setdefault(names.get(int(kind), 'other'), [0, 0.0, 0.0, 0.0])
+      d[0] += 1
+      d[1] += ms
+      d[2] += flops
+      d[3] += nbytes
+    dom = max(by, key=lambda k: by[k][1])
     n, ms, flops, nbytes = by[dom]
     gbs = nbytes / (ms * 1e-3) / 1e9
     tfs = flops / (ms * 1e-3) / 1e12
     traffic = None
-    try:   # per-launch DRAM bytes from the committed ncu --set full capture, if present
-      traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_spconv_tc_traffic.json')))['dram_bytes_per_launch']
-    except Exception:   # noqa: BLE001
-      pass
+    for name in ('r02_spconv_tc_traffic.json', 'r01_spconv_tc_traffic.json'):
+      try:   # per-launch DRAM bytes from the committed ncu --set full capture, if present
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', name)))['dram_bytes_per_launch']
+        break
+      except Exception:   # noqa: BLE001
+        pass
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
-                'launches_per_step': n / K, 'avg_launch_ms': ms / n,
+                'launches_per_step': n / n_prof, 'avg_launch_ms': ms / n,
                 'algorithmic_bytes_per_launch': nbytes / n,
-                'bytes_model': 'SURVEY 8(d) gather-scatter model: P*(Cin+Cout)*4 + 8*P + K_nonempty*Cin*Cout*4'}
+                'bytes_model': 'SURVEY 8(d) gather-scatter model: P*(Cin+Cout)*4 + 8*P + K_nonempty*Cin*Cout*4',
+                'measured_in': f'a serial pass of {n_prof} steps right after the timed region (one pair at a time, CUDA '
+                               'events on the launching stream around every launch); the timed region itself keeps '
+                               f'{inflight} pairs in flight, where an event pair would time two kernels sharing the GPU'}
     roofline_tensor = {'kernel': dom, 'bound': 'tensor', 'achieved': tfs, 'peak': bf16_peak, 'unit': 'TFLOP/s',
                        'frac': tfs / bf16_peak, 'algorithmic_flops_per_launch': flops / n,
                        'note': 'algorithmic fp32 FLOPs 2*P*Cin*Cout; the kernel spends 3 TF32 MMAs per product '
                                '(3xTF32) and TF32 runs at half the bf16 rate, so its ceiling is peak/6'}
-    kernel_share = {k: v[1] / (res['ms']) for k, v in by.items()}
+    kernel_share = {k: v[1] / serial_ms for k, v in by.items()}
+    kernel_share['serial_pass_ms_per_step'] = serial_ms / n_prof
 
   log(f'[bench] value {value:.2f} pairs/s, e2e {e2e:.2f} pairs/s; timing the CPU sample')
   # ---- CPU baseline on a bounded sample --------------------------------------------------------
@@ -455,32 +546,50 @@ def run_ours(args):
   except Exception:   # noqa: BLE001
     pass
 
-  # pose of this arm's first pair (timed `value` loop, step 0) against the CPU oracle's pose of the same pair
-  parity = fixture_parity(res['poses'][0][:16].numpy()) if rank == 0 else None
-  detail = dict(n0=dgr.last_info.get('n0'), n1=dgr.last_info.get('n1'), branch=dgr.last_branch,
-                refine_iterations=dgr.last_info.get('iterations'))
+  # pose of this arm's first pair (timed `value` loop, step 0 = seed 0) against the CPU oracle's pose of the same pair
+  parity = {'end_to_end': fixture_parity(res['poses'][0][:16].numpy()),
+            'final_stage_on_oracle_inputs': stage_isolated_parity(dgr, pairs_dev[0]) if dgr._native_ok() and not strong else None,
+            'config': WORKLOAD,
+            'note': 'end_to_end = register() free-running vs the oracle run of the same pair; the checkpoint is random-init, '
+                    'so its correspondences are unrelated points and the fitted pose is ill-conditioned: a few arg-min flips '
+                    'inside the feature rounding noise move it by centimetres.  final_stage_on_oracle_inputs feeds the '
+                    'oracle\'s correspondences and weights to the CUDA Procrustes + refinement; the other stages are pinned '
+                    'at this size by tests/test_gpu_zzzz_golden_fullsize.py (bit-exact voxels / 6-D coordinates, features '
+                    '<= 5e-5, logits <= 5e-5)'}
+  last = res['last'][2]
+  detail = dict(n0=last.get('n0'), n1=last.get('n1'), branch=res['last'][1], refine_iterations=last.get('iterations'),
+                pairs_in_flight_per_gpu=inflight, native_executor=bool(dgr._native_ok()),
+                host_reads_per_pair=res['reads'] / max(len(res['steps_ms']), 1))
   cfg_out = base_config(world)
-  h2d = int(sum(a.nbytes + b.nbytes for a, b, _ in pairs_host) / POOL)
-  fixed_d2h = 2 * 8 + 8 + 9 * 4 + 8 + 64     # counts, spec flags, coarse-map sizes, wsum, pose
-  line = {'metric': 'scan_pairs_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K,
-          'warmup': args.warmup, 'warmup_steps_run': max(args.warmup, 3) * POOL + POOL + 2 * K, 'ms_per_step': res['ms'] / K, 'higher_is_better': True,
-          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg_out,
+  h2d = int(sum(a.nbytes + b.nbytes for a, b, _ in pairs_host) / len(pairs_host))
+  n_local = len(res['steps_ms'])
+  line = {'metric': 'scan_pairs_per_sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
+          'warmup': args.warmup, 'warmup_steps_run': n_warm + max(min(pool, POOL), 2) + 2 * K,
+          'ms_per_step': res['ms'] / n_local, 'higher_is_better': True,
+          'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+          'config': cfg_out,
           'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d,
-                  'd2h_bytes_per_step': int(res_e2e['d2h'] / K) + fixed_d2h,
-                  'ms_per_step': res_e2e['ms'] / K, 'wall_ms_per_step': 1e3 * res_e2e['wall'] / K},
-          'gpu_launches': int(res['launches']), 'gpu_launches_per_step': res['launches'] / K,
+                  'd2h_bytes_per_step': int(res_e2e['d2h'] / n_local),
+                  'ms_per_step': res_e2e['ms'] / n_local, 'wall_ms_per_step': 1e3 * res_e2e['wall'] / n_local},
+          'gpu_launches': int(res['launches']), 'gpu_launches_per_step': res['launches'] / n_local,
           'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor,
-          'kernel_share_of_step': kernel_share, 'cpu_baseline': cpu, 'parity': parity, 'workload_detail': detail,
-          'wall_ms_per_step': 1e3 * res['wall'] / K,
+          'kernel_share_of_step': kernel_share, 'stage_ms_serial_pass': stage_ms, 'cpu_baseline': cpu, 'parity': parity, 'workload_detail': detail,
+          'wall_ms_per_step': 1e3 * res['wall'] / n_local,
           'host_cgroup_throttled_ms_during_timing': (thr1 - thr0) if thr0 is not None and thr1 is not None else None,
-          'cuda_allocator_events_during_timing': alloc_delta,
-          'host_threads': {'torch_intraop': torch.get_num_threads(), 'usable_cpus': effective_cpus()},
+          'device_arena': arena,
+          'host_threads': {'torch_intraop': torch.get_num_threads(), 'usable_cpus': effective_cpus(),
+                           'affinity': sorted(os.sched_getaffinity(0))[:4] + ['...'] if hasattr(os, 'sched_getaffinity') else None},
+          'per_rank_ms': {'value': res['per_rank_ms'], 'e2e': res_e2e['per_rank_ms']},
           'step_ms': {'min': min(res['steps_ms']), 'median': float(np.median(res['steps_ms'])),
-                      'max': max(res['steps_ms']), 'all': [round(x, 2) for x in res['steps_ms']]},
+                      'max': max(res['steps_ms']), 'all': [round(x, 2) for x in res['steps_ms']],
+                      'note': 'gaps between consecutive pair completions on rank 0 (pairs overlap)'},
           'e2e_step_ms': {'min': min(res_e2e['steps_ms']), 'median': float(np.median(res_e2e['steps_ms'])),
                           'max': max(res_e2e['steps_ms']), 'all': [round(x, 2) for x in res_e2e['steps_ms']]},
           'e2e_with_icp': e2e_icp,
           'published_reference': '0.69 s/pair without safeguard+ICP (reference assets/results.npz, unknown GPU)'}
+  if strong:
+    line['pairs_total'] = args.pairs
+    line['config']['pairs_total'] = args.pairs
   _emit(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
@@ -499,6 +608,9 @@ def main():
                        'of a shared box costs 10-20 %% instead of halving the number; 10 for --impl reference)')
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--pairs', type=int, default=0,
+                  help='BASELINE config 4: register this many pairs (seeds 0..pairs-1) round-robin over the ranks - '
+                       'the same total at every N (strong scaling); 0 = the contract mode (K steps per rank, weak)')
   args = ap.parse_args()
   if args.steps is None:
     args.steps = 10 if args.impl == 'reference' else 100

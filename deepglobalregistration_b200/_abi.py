@@ -66,8 +66,39 @@ SIGNATURES = {
     'dgr_ransac_ws_elems': [_i64, _i64, _p],
     'dgr_ransac_correspondence': [_p, _p, _p, _p, _i64, _f64, _i64, C.c_uint64, _p, _p, _p],
     'dgr_se3_register': [_p, _p, _p, _p, _i64, _f32, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p],
+    # ---- round 2: coordinate planning with device-side counts (csrc/coordplan.cu) ----
+    'dgr_spconv_table_fwd_strided': [_p, _i32, _p, _i32, _p, _i32, _i64, _i64, _p, _p, _p, _p],
+    'dgr_compact_voxel_pair': [_p, _p, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p, _p, _p],
+    'dgr_table_build_unique': [_p, _i64, _p, _i32, _p, _p, _p, _i64, _p],
+    'dgr_coarse_scan_elems': [_i64],
+    'dgr_coarse_maps': [_p, _i64, _p, _i32, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _p],
+    'dgr_bloom2_build': [_p, _i64, _p, _i64, _p],
+    'dgr_kmap_mask_words': [_i64],
+    'dgr_kmap_cnt_elems': [_i32, _i64],
+    'dgr_kmap_probe': [_p, _i64, _p, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p],
+    'dgr_kmap_fill': [_p, _p, _i32, _i64, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p],
+    'dgr_kmap_dense': [_p, _i64, _p, _i32, _p, _p, _p, _i64, _p, _i32, _p, _i64, _p],
+    'dgr_absmax_f32': [_p, _i64, _p, _p],
+    'dgr_spconv_tc_f16_supported': [_i32, _i32],
+    'dgr_pack_weight_f16': [_p, _i32, _i32, _i32, _p, _p, _p],
+    'dgr_spconv_tc_f16_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p],
+    # ---- round 2: native executor (csrc/exec.cu) ----
+    'dgr_ctx_create': [_i32, _p, _p],
+    'dgr_ctx_destroy': [_p],
+    'dgr_ctx_stream': [_p],
+    'dgr_ctx_stats': [_p, _p],
+    'dgr_ctx_profile': [_p, _i32],
+    'dgr_ctx_profile_read': [_p, _p, _i64],
+    'dgr_ctx_stage_times': [_p, _p, _i32],
+    'dgr_net_create': [_i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p],
+    'dgr_net_destroy': [_p],
+    'dgr_net_forward': [_p, _p, _p, _i64, _p, _p],
+    'dgr_pair_register': [_p, _p, _p, _p, _i64, _i32, _p, _i64, _i32, _i32, _f64, _f32, _i32, _p],
+    'dgr_pair_safeguard': [_p, _f64, _i64, C.c_uint64, _i32, _p],
+    'dgr_pair_tap': [_p, _i32, _p, _p, _p],
 }
-_RESTYPES = {'dgr_last_error': C.c_char_p, 'dgr_knn_tc_ws_elems': _i64, 'dgr_launch_count': _i64, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
+_RESTYPES = {'dgr_coarse_scan_elems': _i64, 'dgr_kmap_mask_words': _i64, 'dgr_kmap_cnt_elems': _i64, 'dgr_ctx_stream': C.c_void_p,
+             'dgr_ctx_profile_read': _i64, 'dgr_last_error': C.c_char_p, 'dgr_knn_tc_ws_elems': _i64, 'dgr_launch_count': _i64, 'dgr_spconv_tc_supported': _i32, 'dgr_scan_ws_elems': _i64, 'dgr_kmap_ws_elems': _i64}
 
 _lib = None
 
@@ -413,9 +444,9 @@ def pack_weight_tf32(weight, K, cin, cout):
 # memory (default), 0 = A operand in tensor memory, 2 = CTA pairs with multicast weight tiles,
 # 3 = cta_group::2 (one M = 256 MMA per tile pair, half of every weight tile per CTA; used for
 # cout >= TC_PAIR_MIN_COUT, else 1).  All four are parity-tested.  With the line-coalesced epilogue
-# variant 3 is ~6 % faster on the wide layers (profiles/r01_spconv_tc_experiments.txt); it stays
-# opt-in until the whole GPU suite has run with it.
-TC_VARIANT = int(os.environ.get('DGR_TC_VARIANT', '1'))
+# variant 3 is ~6 % faster on the wide layers (profiles/r01_spconv_tc_experiments.txt); default since
+# round 2 (the whole GPU suite runs with it).
+TC_VARIANT = int(os.environ.get('DGR_TC_VARIANT', '3'))
 TC_PAIR_MIN_COUT = int(os.environ.get('DGR_TC_PAIR_MIN_COUT', '128'))
 
 # When set to a list, every sparse-convolution launch appends
@@ -456,6 +487,22 @@ def spconv_tc_fwd(feat, weight_t, km, out, passes=3, cluster=None):
   _conv_profiled('spconv_tc_kernel', km, cin, cout, lambda: call(
       'dgr_spconv_tc_fwd', ptr(feat), cin, ptr(weight_t), cout, ptr(km.in_idx), ptr(km.out_idx),
       ptr(km.kofs), ptr(tk), ptr(ts), nt, TILE_ROWS, int(passes), cluster, ptr(out), stream()))
+  return out
+
+
+def spconv_tc_f16_fwd(feat, weight, km, out, amax=None):
+  """3xFP16 cta_group::2 convolution (weight: the fp32 [K, cin, cout] kernel; packed per call - test helper)."""
+  _chk(feat, torch.float32, 'feat'); _chk(weight, torch.float32, 'weight'); _chk(out, torch.float32, 'out')
+  cin, cout = feat.shape[1], out.shape[1]
+  packed = torch.empty(4 * km.K * cin * cout, dtype=torch.uint8, device=feat.device)
+  wscale = torch.empty(2, dtype=torch.float32, device=feat.device)
+  call('dgr_pack_weight_f16', ptr(weight), km.K, cin, cout, ptr(packed), ptr(wscale), stream())
+  if amax is None:
+    amax = torch.empty(1, dtype=torch.float32, device=feat.device)
+    call('dgr_absmax_f32', ptr(feat), feat.numel(), ptr(amax), stream())
+  tk, ts, nt = km.paired_tiles()
+  call('dgr_spconv_tc_f16_fwd', ptr(feat), cin, ptr(packed), cout, ptr(km.in_idx), ptr(km.out_idx), ptr(km.kofs),
+       ptr(tk), ptr(ts), nt, TILE_ROWS, ptr(amax), ptr(wscale), ptr(out), stream())
   return out
 
 

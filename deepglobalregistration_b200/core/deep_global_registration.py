@@ -12,7 +12,10 @@ import os
 import numpy as np
 import torch
 
-from .. import _abi, shims
+import threading
+import time
+
+from .. import _abi, native, shims
 from ..me import SparseTensor
 from ..me.coords import CoordinateManager, KEY_MARGIN
 from ..model import load_model
@@ -65,7 +68,21 @@ class DeepGlobalRegistration:
         in_channels=6 if nc.inlier_feature_type == 'coords' else 1, out_channels=1,
         conv1_kernel_size=nc['inlier_conv1_kernel_size'], normalize_feature=False, D=6)
     self._pinned = {}
+    # native executor (csrc/exec.cu): one C call per pair; built lazily, rebuilt when the weights change
+    self.use_native = os.environ.get('DGR_NATIVE', '1') != '0'
+    self._native_nets = None
+    self._native_ctx = []
+    self._last_ctx = None
+    self._last_sel_value = None
     self._log('=> loading finished')
+
+  @property
+  def _last_sel(self):
+    """Indices of the raw points kept by the last voxelisation: of the cloud preprocess() saw last, or - after
+    a native register() - of both clouds of the pair (cloud 1's offset by the size of cloud 0)."""
+    if self._last_ctx is not None:
+      return self._last_ctx.tap('sel')
+    return self._last_sel_value
 
   def _build_network(self, name, weights, in_channels, out_channels, conv1_kernel_size, normalize_feature, D):
     cls = load_model(name)
@@ -123,7 +140,7 @@ class DeepGlobalRegistration:
     xyz_sel = dxyz[sel.long()].float()
     # the dedup table already maps voxel key -> row of `coords`: hand it to SparseTensor
     coords._dgr_manager = CoordinateManager(_parts=(coords, spec, table))
-    self._last_sel = sel
+    self._last_sel_value, self._last_ctx = sel, None
     feats = torch.ones(npts, 1, device=self.device)
     return xyz_sel, coords, feats
 
@@ -199,8 +216,125 @@ class DeepGlobalRegistration:
                                       num_hyp=self.safeguard_max_iteration, seed=self.safeguard_seed)
 
   # ---------------------------------------------------------------------------------------
+  # ---------------------------------------------------------------------------------------
+  # native path: the whole pair in one C call (three host reads), see csrc/exec.cu
+  # ---------------------------------------------------------------------------------------
+  def _param_version(self):
+    return tuple(p._version for m in (self.fcgf_model, self.inlier_model) for p in list(m.parameters()) + list(m.buffers()))
+
+  def native_networks(self):
+    """(fcgf, inlier) native layer tables, rebuilt when a parameter or BatchNorm statistic changed."""
+    ver = self._param_version()
+    if self._native_nets is None or self._native_nets[0] != ver:
+      if self._native_nets is not None:
+        for ctx in self._native_ctx:       # nothing may still run on the old weights
+          torch.cuda.synchronize(self.device)
+        for n in self._native_nets[1:]:
+          n.close()
+      self._native_nets = (ver, native.Net(self.fcgf_model, self.device), native.Net(self.inlier_model, self.device))
+    return self._native_nets[1], self._native_nets[2]
+
+  def native_context(self, k=0):
+    while len(self._native_ctx) <= k:
+      self._native_ctx.append(native.Context(self.device))
+    return self._native_ctx[k]
+
+  def _native_ok(self):
+    return (self.use_native and self.config.inlier_feature_type == 'ones' and
+            self.safeguard_method == 'correspondence' and hasattr(self.fcgf_model, 'CHANNELS'))
+
+  @staticmethod
+  def _points(pcd):
+    if isinstance(pcd, (np.ndarray, torch.Tensor)):
+      return pcd
+    if hasattr(pcd, 'points'):            # open3d.geometry.PointCloud
+      return np.asarray(pcd.points)
+    raise Exception('Unrecognized pcd type')
+
+  def _register_native(self, ctx, xyz0, xyz1):
+    """-> (T 4x4 float64, branch, info).  Thread-safe across distinct contexts."""
+    fcgf, inl = self.native_networks()
+    res = native.pair_register(ctx, fcgf, inl, self._points(xyz0), self._points(xyz1), self.voxel_size,
+                               self.clip_weight_thresh, self.use_icp)
+    wsum, n0, n1 = float(res[16]), int(res[40]), int(res[41])
+    info = dict(wsum=wsum, n0=n0, n1=n1, host_reads=int(res[42]), d2h_bytes=int(res[43]) + 64 * 8)
+    T = np.identity(4)
+    if wsum >= max(200, n0 * 0.05):
+      T[0:3, 0:3] = res[:9].reshape(3, 3)
+      T[0:3, 3] = res[9:12]
+      branch = 'procrustes'
+      info.update(iterations=int(res[12]), loss=float(res[13]), break_count=int(res[14]), n_active=int(res[15]))
+      icp = res[17:37] if self.use_icp else None
+    else:
+      # > Case 1: Safeguard RANSAC + (optional) ICP (reference :302-315), one more host read
+      branch = 'safeguard'
+      sg = native.pair_safeguard(ctx, 2 * self.voxel_size, self.safeguard_max_iteration, self.safeguard_seed,
+                                 self.use_icp)
+      T = sg[:16].reshape(4, 4).copy()
+      info.update(ransac_fitness=float(sg[16]), ransac_inlier_rmse=float(sg[17]), ransac_hypothesis=int(sg[18]),
+                  ransac_inliers=int(sg[19]), host_reads=info['host_reads'] + 1)
+      icp = sg[20:40] if self.use_icp else None
+    if icp is not None:
+      T = icp[:16].reshape(4, 4).copy()
+      info.update(icp_fitness=float(icp[16]), icp_inlier_rmse=float(icp[17]), icp_iterations=int(icp[18]))
+    info['t_done'] = time.perf_counter()
+    return T, branch, info
+
   def register(self, xyz0, xyz1, inlier_thr=0.00):
-    """Main algorithm.  -> 4x4 float64 ndarray mapping cloud 0 into cloud 1's frame."""
+    """Main algorithm.  -> 4x4 float64 ndarray mapping cloud 0 into cloud 1's frame
+    (core/deep_global_registration.py:238-324)."""
+    if not self._native_ok():
+      return self.register_stagewise(xyz0, xyz1, inlier_thr)
+    self.reg_timer.tic()
+    ctx = self.native_context(0)
+    T, branch, info = self._register_native(ctx, xyz0, xyz1)
+    self.last_branch, self.last_info, self._last_ctx = branch, info, ctx
+    wsum_threshold = max(200, info['n0'] * 0.05)
+    sign = '>=' if branch == 'procrustes' else '<'
+    self._log(f'=> Weighted sum {info["wsum"]:.2f} {sign} threshold {wsum_threshold}')
+    t = self.reg_timer.toc()
+    self._log(f'=> DGR takes {t:.2} s' if branch == 'procrustes' else f'=> Safeguard takes {t:.2} s')
+    return T
+
+  def register_batch(self, pairs, inflight=2):
+    """Register independent pairs with `inflight` of them in flight on this GPU (one host thread, stream
+    and arena each): the latency-bound stages and host reads of one pair overlap the convolutions
+    of the other.  pairs: [(xyz0, xyz1), ...] (arrays, tensors, point clouds, or callables returning such a
+    tuple - e.g. file readers).  -> [(T, branch, info), ...] in input order."""
+    if not self._native_ok() or inflight <= 1 or len(pairs) <= 1:
+      out = []
+      for pr in pairs:
+        a, b = pr() if callable(pr) else pr
+        T = self.register(a, b)
+        out.append((T, self.last_branch, dict(self.last_info)))
+      return out
+    self.native_networks()            # built once, on this thread
+    ctxs = [self.native_context(k) for k in range(inflight)]
+    results, errors = [None] * len(pairs), []
+
+    def worker(k):
+      try:
+        torch.cuda.set_device(self.device)
+        for i in range(k, len(pairs), inflight):
+          a, b = pairs[i]() if callable(pairs[i]) else pairs[i]
+          results[i] = self._register_native(ctxs[k], a, b)
+      except BaseException as e:   # noqa: BLE001
+        errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(inflight)]
+    for t in threads:
+      t.start()
+    for t in threads:
+      t.join()
+    if errors:
+      raise errors[0]
+    self.last_branch, self.last_info = results[-1][1], results[-1][2]
+    self._last_ctx = ctxs[(len(pairs) - 1) % inflight]
+    return results
+
+  def register_stagewise(self, xyz0, xyz1, inlier_thr=0.00):
+    """The same algorithm driven stage by stage from Python through the operator-level C ABI (round 1's
+    path): every inlier feature type, and the reference's own stage methods, go through here."""
     self.reg_timer.tic()
     _abi.refresh_stream()
     with torch.no_grad():

@@ -21,15 +21,22 @@ void dgr_note_launches(int n);   // bookkeeping for dgr_launch_count()
 
 #define DGR_LAUNCH_CHECK() DGR_CUDA_CHECK(cudaGetLastError())
 
-// Opt a kernel in to `bytes` of dynamic shared memory - once per call site (and again only if a
-// later launch needs more), not before every launch: cudaFuncSetAttribute is a driver call that
-// takes the context lock.
+// Opt a kernel in to large dynamic shared memory - ONCE per call site, to the device maximum (227 KB on
+// sm_100), whatever this launch needs: the attribute is per function, not per launch, so two host threads
+// (two pairs in flight) that set launch-specific sizes would race (thread A sets 100 KB, thread B sets 60 KB,
+// A's launch then fails with "invalid argument").  Setting the same maximum twice is harmless.
+#define DGR_SMEM_OPTIN_MAX 232448
 #define DGR_ENSURE_SMEM(func, bytes)                                                                 \
   do {                                                                                               \
-    static std::atomic<int> cur_smem_{0};                                                            \
-    if ((int)(bytes) > cur_smem_.load(std::memory_order_relaxed)) {                                  \
-      DGR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
-      cur_smem_.store((int)(bytes), std::memory_order_relaxed);                                      \
+    static std::atomic<int> done_smem_{0};                                                           \
+    if ((size_t)(bytes) > (size_t)DGR_SMEM_OPTIN_MAX) {                                              \
+      dgr_set_error("%s:%d: %zu bytes of shared memory requested", __FILE__, __LINE__, (size_t)(bytes)); \
+      return DGR_ERR_ARG;                                                                            \
+    }                                                                                                \
+    if ((size_t)(bytes) > 48 * 1024 && !done_smem_.load(std::memory_order_acquire)) {                \
+      DGR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                          DGR_SMEM_OPTIN_MAX));                                      \
+      done_smem_.store(1, std::memory_order_release);                                                \
     }                                                                                                \
   } while (0)
 

@@ -247,7 +247,7 @@ linear_fwd_kernel(const float* __restrict__ a, int ca, const float* __restrict__
 template <int COUT>
 __global__ void __launch_bounds__(kThreads)
 spconv_table_kernel(const float* __restrict__ in_feat, int cin, const float* __restrict__ weight,
-                    const int32_t* __restrict__ nbr, int K, int64_t n_out,
+                    const int32_t* __restrict__ nbr, int K, int64_t n_out, int64_t nbr_stride,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     float* __restrict__ out) {
   extern __shared__ __align__(16) float w_s[];   // [kc, cin, COUT] chunk of the weights
@@ -270,7 +270,7 @@ spconv_table_kernel(const float* __restrict__ in_feat, int cin, const float* __r
         float x0[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          idx[u] = (kb + u < kn) ? __ldcs(nbr + (int64_t)(k0 + kb + u) * n_out + j) : -1;
+          idx[u] = (kb + u < kn) ? __ldcs(nbr + (int64_t)(k0 + kb + u) * nbr_stride + j) : -1;
 #pragma unroll
         for (int u = 0; u < 8; ++u) x0[u] = idx[u] >= 0 ? __ldg(in_feat + (int64_t)idx[u] * cin) : 0.f;
 #pragma unroll
@@ -403,23 +403,24 @@ int32_t dgr_spconv_fwd(const float* in_feat, int32_t cin, const float* weight, i
   return DGR_OK;
 }
 
-int32_t dgr_spconv_table_fwd(const float* in_feat, int32_t cin, const float* weight, int32_t cout,
-                             const int32_t* nbr, int32_t K, int64_t n_out, const float* scale,
-                             const float* shift, float* out, void* stream) {
+int32_t dgr_spconv_table_fwd_strided(const float* in_feat, int32_t cin, const float* weight, int32_t cout,
+                                     const int32_t* nbr, int32_t K, int64_t n_out, int64_t nbr_stride,
+                                     const float* scale, const float* shift, float* out, void* stream) {
   DGR_ARG_CHECK(cin >= 1 && cin <= 8, "table convolution supports 1..8 input channels");
   DGR_ARG_CHECK((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+  DGR_ARG_CHECK(nbr_stride >= n_out, "row stride of the neighbour table below its row count");
   if (n_out == 0) return DGR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = 44 * 1024;
   const unsigned blocks = dgr_blocks(n_out, kThreads);
   if (cout == 32)
-    spconv_table_kernel<32><<<blocks, kThreads, smem, st>>>(in_feat, cin, weight, nbr, K, n_out, scale,
+    spconv_table_kernel<32><<<blocks, kThreads, smem, st>>>(in_feat, cin, weight, nbr, K, n_out, nbr_stride, scale,
                                                            shift, out);
   else if (cout == 64)
-    spconv_table_kernel<64><<<blocks, kThreads, smem, st>>>(in_feat, cin, weight, nbr, K, n_out, scale,
+    spconv_table_kernel<64><<<blocks, kThreads, smem, st>>>(in_feat, cin, weight, nbr, K, n_out, nbr_stride, scale,
                                                            shift, out);
   else if (cout == 16)
-    spconv_table_kernel<16><<<blocks, kThreads, smem, st>>>(in_feat, cin, weight, nbr, K, n_out, scale,
+    spconv_table_kernel<16><<<blocks, kThreads, smem, st>>>(in_feat, cin, weight, nbr, K, n_out, nbr_stride, scale,
                                                            shift, out);
   else {
     dgr_set_error("dgr_spconv_table_fwd: cout must be 16, 32 or 64 (got %d)", cout);
@@ -428,6 +429,12 @@ int32_t dgr_spconv_table_fwd(const float* in_feat, int32_t cin, const float* wei
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
+}
+
+int32_t dgr_spconv_table_fwd(const float* in_feat, int32_t cin, const float* weight, int32_t cout,
+                             const int32_t* nbr, int32_t K, int64_t n_out, const float* scale,
+                             const float* shift, float* out, void* stream) {
+  return dgr_spconv_table_fwd_strided(in_feat, cin, weight, cout, nbr, K, n_out, n_out, scale, shift, out, stream);
 }
 
 int32_t dgr_linear_fwd(const float* a, int32_t ca, const float* b, int32_t cb, int64_t n,

@@ -22,6 +22,7 @@
 // cached per layer by the host): per (offset, 32-channel chunk) one contiguous slab holding the
 // TF32 hi tile and the lo tile in shared-memory image order, streamed by a single
 // cp.async.bulk (TMA engine) per stage - the loader threads only touch the gathered rows.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -30,6 +31,12 @@
 namespace {
 
 using namespace tc;
+
+#define DGR_TRY_RC(expr)             \
+  do {                              \
+    int32_t rc__ = (expr);          \
+    if (rc__ != DGR_OK) return rc__; \
+  } while (0)
 
 constexpr int kLoaderWarps = 8;
 constexpr int kLoaderThreads = kLoaderWarps * 32;   // warps 0..7: gather + TF32 split
@@ -49,6 +56,36 @@ __device__ __forceinline__ void split_store(float4 v, unsigned char* hi_tile, un
   l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
   *reinterpret_cast<float4*>(hi_tile + off) = h;
   *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+// 3xFP16 split (cta_group::2 kernel, kF16): fp16 carries the same 11 significant bits as TF32 at half the
+// bytes and twice the tensor rate.  x is first scaled by a power of two `sx` (exact) that maps the tensor's
+// absolute maximum into [2^14, 2^15) - below fp16's 65504, far above its 2^-14 normal floor - then split into
+// hi = fp16(x'), lo = fp16(x' - hi): the same hi*hi + lo*hi + hi*lo products as 3xTF32, 2^-21 relative
+// (an element more than 2^17 below the tensor's maximum loses bits of its lo part: <= 2^-39 of the maximum).
+__device__ __forceinline__ void split_store_f16(float4 a, float4 b, float sx, unsigned char* hi_tile,
+                                                unsigned char* lo_tile, uint32_t off) {
+  const float x[8] = {a.x * sx, a.y * sx, a.z * sx, a.w * sx, b.x * sx, b.y * sx, b.z * sx, b.w * sx};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// power of two that maps `amax` into [2^14, 2^15); 1 for amax == 0 / non-finite
+__device__ __forceinline__ float f16_scale_for(float amax) {
+  const uint32_t b = __float_as_uint(amax);
+  const int e = (int)((b >> 23) & 255u);
+  if (e == 0 || e == 255) return 1.f;
+  int se = 14 - (e - 127) + 127;
+  se = se < 1 ? 1 : (se > 254 ? 254 : se);
+  return __uint_as_float((uint32_t)se << 23);
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -622,6 +659,15 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -629,13 +675,18 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <int kPD>
+// kF16: 3xFP16 instead of 3xTF32 (64 channels per 128-byte stage row; `wt` then holds the fp16 slabs of
+// dgr_pack_weight_f16, amax_in the input tensor's absolute maximum, w_inv_scale the inverse of the weight scale)
+template <int kPD, bool kF16>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* __restrict__ wt, int cout,
                       const int32_t* __restrict__ in_idx, const int32_t* __restrict__ out_idx,
                       const int32_t* __restrict__ kofs, const int32_t* __restrict__ tile_k,
                       const int32_t* __restrict__ tile_start, int n_tiles, int n_stages, int tmem_cols,
-                      int passes, int epi, float* __restrict__ out) {
+                      int passes, int epi, const float* __restrict__ amax_in,
+                      const float* __restrict__ w_inv_scale, float* __restrict__ out) {
+  constexpr int kCh = kF16 ? 64 : kChunk;        // channels per stage (one 128-byte swizzle row)
+  constexpr int kV = kF16 ? 2 : 1;               // float4 loads per (thread, row, chunk)
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   Tc2Shared& sh = *reinterpret_cast<Tc2Shared*>(smem_dyn);
   unsigned char* stage0 = reinterpret_cast<unsigned char*>(
@@ -645,7 +696,7 @@ spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* _
   const int stage_bytes = 2 * kATileBytes + 2 * b_half_bytes;
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
-  const int n_chunks = cin / kChunk;
+  const int n_chunks = cin / kCh;
   const uint32_t acc_stride = (uint32_t)tmem_cols >> 1;
   const uint32_t rank = cluster_ctarank();
   const int n_pairs = n_tiles >> 1;
@@ -691,21 +742,24 @@ spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* _
         src[i] = (r < nrows) ? __ldg(in_idx + q0 + r) : -1;
       }
     };
-    auto load_a = [&](const int (&src)[4], int c, float4 (&v)[4]) {
+    auto load_a = [&](const int (&src)[4], int c, float4 (&v)[4][kV]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        v[i] = src[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)src[i] * cin + c * kChunk +
-                                                                    piece * 4))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kV; ++u)
+          v[i][u] = src[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)src[i] * cin + c * kCh +
+                                                                         piece * (4 * kV) + 4 * u))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    const float sx = kF16 ? f16_scale_for(__ldg(amax_in)) : 1.f;
     uint32_t it = 0;
     const int tstep = 2 * pair_step;             // this CTA's tiles: 2 * pair + rank
-    float4 q[kPD + 1][4];                        // gather queue, kPD chunks ahead (see spconv_tc_kernel)
+    float4 q[kPD + 1][4][kV];                    // gather queue, kPD chunks ahead (see spconv_tc_kernel)
     int pf_tile = 2 * pair0 + (int)rank, pf_c = 0;
     int pf_src[4], pf_nsrc[4];
     if (pf_tile < n_tiles) load_rows(pf_tile, pf_src);
     if (pf_tile + tstep < n_tiles) load_rows(pf_tile + tstep, pf_nsrc);
-    auto pf_issue = [&](float4 (&v)[4]) {
+    auto pf_issue = [&](float4 (&v)[4][kV]) {
       if (pf_tile < n_tiles) load_a(pf_src, pf_c, v);
       if (++pf_c == n_chunks) {
         pf_c = 0;
@@ -737,13 +791,18 @@ spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* _
                    smem_u32(&sh.full[s]));
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_store(q[0][i], a_hi, a_lo, a_off + i * 4096);
+        for (int i = 0; i < 4; ++i) {
+          if (kF16) split_store_f16(q[0][i][0], q[0][i][kV - 1], sx, a_hi, a_lo, a_off + i * 4096);
+          else split_store(q[0][i][0], a_hi, a_lo, a_off + i * 4096);
+        }
         fence_proxy_async();
         mbar_arrive(smem_u32(&sh.full[s]));
 #pragma unroll
         for (int d = 0; d < kPD; ++d)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) q[d][i] = q[d + 1][i];
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int u = 0; u < kV; ++u) q[d][i][u] = q[d + 1][i][u];
       }
     }
   } else if (warp == kMmaWarp) {
@@ -762,7 +821,9 @@ spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* _
     } else {
       // ============================ leader: MMA issuer for the pair =======================
       // instruction descriptor: D = F32, A = B = TF32, both K-major, N = cout, M = 256 (128 per CTA)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cout >> 3) << 17) |
+      // (kF16: A = B = F16, format code 0; K per instruction 16 halves = the same 32 bytes)
+      const uint32_t fmt = kF16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(cout >> 3) << 17) |
                              ((uint32_t)((2 * kTileM) >> 4) << 24);
       uint32_t it = 0, tile_iter = 0;
       for (int pair = pair0; pair < n_pairs; pair += pair_step, ++tile_iter) {
@@ -782,13 +843,21 @@ spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* _
             const uint32_t b_hi = a_lo + kATileBytes;
             const uint32_t b_lo = b_hi + b_half_bytes;
 #pragma unroll
-            for (int ks = 0; ks < kChunk / 8; ++ks) {
+            for (int ks = 0; ks < 4; ++ks) {       // 4 k-steps of 32 bytes per 128-byte row
               const uint32_t ko = ks * 32;
               const uint64_t dbh = umma_desc(b_hi + ko);
-              tc_mma_tf32_pair(tmem_d, umma_desc(a_hi + ko), dbh, idesc, (c | ks) != 0);
-              if (passes == 3) {
-                tc_mma_tf32_pair(tmem_d, umma_desc(a_lo + ko), dbh, idesc, 1);
-                tc_mma_tf32_pair(tmem_d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1);
+              if (kF16) {
+                tc_mma_f16_pair(tmem_d, umma_desc(a_hi + ko), dbh, idesc, (c | ks) != 0);
+                if (passes == 3) {
+                  tc_mma_f16_pair(tmem_d, umma_desc(a_lo + ko), dbh, idesc, 1);
+                  tc_mma_f16_pair(tmem_d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1);
+                }
+              } else {
+                tc_mma_tf32_pair(tmem_d, umma_desc(a_hi + ko), dbh, idesc, (c | ks) != 0);
+                if (passes == 3) {
+                  tc_mma_tf32_pair(tmem_d, umma_desc(a_lo + ko), dbh, idesc, 1);
+                  tc_mma_tf32_pair(tmem_d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1);
+                }
               }
             }
             tc_commit_pair(smem_u32(&sh.empty[s]));                       // frees the stage in both CTAs
@@ -802,6 +871,8 @@ spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* _
     // ================================ epilogue (both CTAs, own 128 rows) ==================
     const int lane_grp = warp & 3;
     unsigned char* epi_stage = stage0 + (size_t)n_stages * stage_bytes + (warp - kLoaderWarps - 1) * 4096;
+    // kF16: the accumulator holds (sx * x) . (sw * w); both scales are powers of two, undone exactly here
+    const float inv = kF16 ? __ldg(w_inv_scale) / f16_scale_for(__ldg(amax_in)) : 1.f;
     uint32_t tile_iter = 0;
     for (int pair = pair0; pair < n_pairs; pair += pair_step, ++tile_iter) {
       const int tile = 2 * pair + (int)rank;
@@ -818,12 +889,20 @@ spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* _
       for (; col + 32 <= cout; col += 32) {
         uint32_t v[32];
         tc_ld32(taddr + col, v);
+        if (kF16) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * inv);
+        }
         if (epi) scatter32_lines(epi_stage, lane, out, cout, col, j, v);
         else scatter32_rows(out, cout, col, j, v);
       }
       if (col < cout) {   // cout % 32 == 16
         uint32_t v[16];
         tc_ld16(taddr + col, v);
+        if (kF16) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * inv);
+        }
         if (j >= 0) {
           float* dst = out + (size_t)j * cout + col;
 #pragma unroll
@@ -868,6 +947,51 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cin, int cou
   const int off = n * 32 + ((q ^ (n & 7)) << 2);                 // floats
   *reinterpret_cast<float4*>(slab + off) = h;
   *reinterpret_cast<float4*>(slab + (size_t)cout * 32 + off) = l;
+}
+
+// |x| maximum of a tensor as float bits (non-negative floats order like unsigned ints)
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(x[(n4 << 2) + threadIdx.x]));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// W[K, cin, cout] fp32 -> packed[K][cin/64][2][cout][64 halves]: per (kappa, 64-channel chunk) the K-major
+// SWIZZLE_128B image of the B operand, fp16 hi tile then fp16 lo tile of (sw * W); scale[0] = 1 / sw.
+__global__ void pack_weight_f16_kernel(const float* __restrict__ w, int cin, int cout, const float* __restrict__ amax,
+                                       unsigned char* __restrict__ packed, float* __restrict__ scale) {
+  const int n_chunks = cin / 64;
+  const int64_t total = (int64_t)n_chunks * cout * 8;          // 16-byte pieces (8 halves) per kappa
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float sw = f16_scale_for(*amax);
+  if (e == 0 && blockIdx.y == 0) scale[0] = 1.f / sw;
+  if (e >= total) return;
+  const int kappa = blockIdx.y;
+  const int n = (int)(e % cout);
+  const int q = (int)((e / cout) % 8);
+  const int ch = (int)(e / ((int64_t)cout * 8));
+  const float* src = w + ((size_t)kappa * cin + ch * 64 + q * 8) * cout + n;
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float x0 = src[(size_t)(2 * i) * cout] * sw, x1 = src[(size_t)(2 * i + 1) * cout] * sw;
+    const __half2 hh = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  unsigned char* slab = packed + ((size_t)kappa * n_chunks + ch) * 2 * cout * 128;
+  const int off = n * 128 + ((q ^ (n & 7)) << 4);
+  *reinterpret_cast<uint4*>(slab + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(slab + (size_t)cout * 128 + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 }  // namespace
@@ -955,8 +1079,8 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
     const size_t smem2 = sizeof(Tc2Shared) + 1024 + (size_t)ns2 * sb2 + kEpiStageBytes;
     grid = sms & ~1;
     if (grid > n_tiles) grid = n_tiles;
-    auto pair_kernel = pd == 1 ? spconv_tc_pair_kernel<1> : pd == 2 ? spconv_tc_pair_kernel<2> : spconv_tc_pair_kernel<3>;
-    DGR_CUDA_CHECK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    auto pair_kernel = pd == 1 ? spconv_tc_pair_kernel<1, false> : pd == 2 ? spconv_tc_pair_kernel<2, false> : spconv_tc_pair_kernel<3, false>;
+    DGR_ENSURE_SMEM(pair_kernel, smem2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreadsTC);
@@ -971,13 +1095,13 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
     cfg.numAttrs = 1;
     DGR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, pair_kernel, in_feat, (int)cin, weight_t, (int)cout, in_idx,
                                       out_idx, kofs, tile_k, tile_start, (int)n_tiles, ns2, tmem_cols,
-                                      (int)passes, epi, out));
+                                      (int)passes, epi, (const float*)nullptr, (const float*)nullptr, out));
   } else if (cluster == 2) {
     // CTA pairs on two tiles of the same offset, B tiles multicast to both (paired tile list)
     DGR_ARG_CHECK(n_tiles % 2 == 0, "a paired tile list has an even number of tiles");
     grid &= ~1;
     auto k2 = pd == 1 ? spconv_tc_kernel<2, 1> : pd == 2 ? spconv_tc_kernel<2, 2> : spconv_tc_kernel<2, 3>;
-    DGR_CUDA_CHECK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DGR_ENSURE_SMEM(k2, smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreadsTC);
@@ -995,11 +1119,98 @@ int32_t dgr_spconv_tc_fwd(const float* in_feat, int32_t cin, const float* weight
                                       (int)passes, epi, out));
   } else {
     auto k1 = pd == 1 ? spconv_tc_kernel<1, 1> : pd == 2 ? spconv_tc_kernel<1, 2> : spconv_tc_kernel<1, 3>;
-    DGR_CUDA_CHECK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DGR_ENSURE_SMEM(k1, smem);
     k1<<<grid, kThreadsTC, smem, st>>>(in_feat, cin, weight_t, cout, in_idx, out_idx, kofs,
                                                         tile_k, tile_start, n_tiles, n_stages, tmem_cols, passes,
                                                         epi, out);
   }
+  dgr_note_launches(1);
+  DGR_LAUNCH_CHECK();
+  return DGR_OK;
+}
+
+// amax[0] (device float) = max |x| over n floats; the slot is zeroed by the call.
+int32_t dgr_absmax_f32(const float* x, int64_t n, float* amax, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DGR_CUDA_CHECK(cudaMemsetAsync(amax, 0, sizeof(float), st));
+  if (n <= 0) return DGR_OK;
+  unsigned blocks = dgr_blocks(n / 4 + 1, 256);
+  if (blocks > 592) blocks = 592;
+  absmax_kernel<<<blocks, 256, 0, st>>>(x, n, reinterpret_cast<unsigned*>(amax));
+  dgr_note_launches(1);
+  DGR_LAUNCH_CHECK();
+  return DGR_OK;
+}
+
+// 1 if dgr_spconv_tc_f16_fwd supports the shape: the cta_group::2 kernel in 3xFP16 mode
+int32_t dgr_spconv_tc_f16_supported(int32_t cin, int32_t cout) {
+  return (cin >= 64 && cin % 64 == 0 && cout >= 32 && cout <= 256 && cout % 32 == 0) ? 1 : 0;
+}
+
+// W[K, cin, cout] -> fp16 hi|lo slabs [K][cin/64][2][cout][64] (4 * K * cin * cout BYTES, half of the TF32
+// slabs) of sw * W with sw the power of two that maps max|W| into [2^14, 2^15); scale_ws (device float[2]):
+// [0] = 1 / sw (read by the kernel's epilogue), [1] = max |W| (workspace).
+int32_t dgr_pack_weight_f16(const float* w, int32_t K, int32_t cin, int32_t cout, void* packed, float* scale_ws,
+                            void* stream) {
+  DGR_ARG_CHECK(K >= 1 && K <= 65535 && dgr_spconv_tc_f16_supported(cin, cout), "bad weight shape");
+  DGR_TRY_RC(dgr_absmax_f32(w, (int64_t)K * cin * cout, scale_ws + 1, stream));
+  const int64_t per_k = (int64_t)(cin / 64) * cout * 8;
+  dim3 grid(dgr_blocks(per_k, 256), K);
+  pack_weight_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, cin, cout, scale_ws + 1, (unsigned char*)packed,
+                                                               scale_ws);
+  dgr_note_launches(1);
+  DGR_LAUNCH_CHECK();
+  return DGR_OK;
+}
+
+// dgr_spconv_tc_fwd's cta_group::2 kernel with every product evaluated as hi*hi + lo*hi + hi*lo on FP16 splits
+// of power-of-two-scaled operands (same 2^-21 accuracy as 3xTF32, half the weight bytes, twice the tensor rate).
+// amax_in: device float = max |in_feat| (dgr_absmax_f32, or an upper bound); w_scale: scale_ws of
+// dgr_pack_weight_f16.  Needs the PAIRED tile list (dgr_kernel_map_tiles(pair = 1)).
+int32_t dgr_spconv_tc_f16_fwd(const float* in_feat, int32_t cin, const void* weight_h, int32_t cout,
+                              const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,
+                              const int32_t* tile_k, const int32_t* tile_start, int32_t n_tiles, int32_t tile_rows,
+                              const float* amax_in, const float* w_scale, float* out, void* stream) {
+  DGR_ARG_CHECK(tile_rows == kTileM, "tile_rows must be 128");
+  DGR_ARG_CHECK(dgr_spconv_tc_f16_supported(cin, cout), "shape not supported by the 3xFP16 path");
+  DGR_ARG_CHECK(n_tiles % 2 == 0, "a paired tile list has an even number of tiles");
+  DGR_ARG_CHECK(amax_in != nullptr && w_scale != nullptr, "scales missing");
+  if (n_tiles == 0) return DGR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  static const int pd = [] {
+    const char* e = getenv("DGR_TC_PREFETCH");
+    int v = e ? atoi(e) : 1;
+    return v < 1 ? 1 : (v > 2 ? 2 : v);
+  }();
+  int acc_cols = 32;
+  while (acc_cols < cout) acc_cols <<= 1;
+  const int tmem_cols = 2 * acc_cols;
+  int dev = 0, sms = 148;
+  DGR_CUDA_CHECK(cudaGetDevice(&dev));
+  DGR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sb2 = 2 * kATileBytes + cout * 128;
+  int ns2 = (200 * 1024) / sb2;
+  if (ns2 > 4) ns2 = 4;
+  const size_t smem2 = sizeof(Tc2Shared) + 1024 + (size_t)ns2 * sb2 + kEpiStageBytes;
+  int grid = sms & ~1;
+  if (grid > n_tiles) grid = n_tiles;
+  auto kern = pd == 1 ? spconv_tc_pair_kernel<1, true> : spconv_tc_pair_kernel<2, true>;
+  DGR_ENSURE_SMEM(kern, smem2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsTC);
+  cfg.dynamicSmemBytes = smem2;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DGR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, in_feat, (int)cin, (const float*)weight_h, (int)cout, in_idx, out_idx,
+                                    kofs, tile_k, tile_start, (int)n_tiles, ns2, tmem_cols, 3, 1, amax_in, w_scale,
+                                    out));
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;

@@ -62,18 +62,32 @@ def _cloud(item):
   return item
 
 
-def register_pairs(dgr, pairs, device=None):
+def register_pairs(dgr, pairs, device=None, inflight=2):
   """Register this rank's share of `pairs` ([(xyz0, xyz1), ...]; members may be file paths) with
-  `dgr` and gather all results.  Returns [len(pairs), 20] float64, identical on every rank.  The
-  milliseconds column times register() only, not the file reads."""
+  `dgr` and gather all results.  Returns [len(pairs), 20] float64, identical on every rank.  With a
+  DeepGlobalRegistration that has register_batch, `inflight` pairs are kept in flight on the GPU (one host
+  thread, stream and arena each); file members are read by the worker that registers them, so a rank only
+  ever loads its own share.  The milliseconds column is the time between consecutive completions on this
+  rank (its inverse is the rank's throughput), file reads included."""
   world = dist.get_world_size() if dist.is_initialized() else 1
   rank = dist.get_rank() if dist.is_initialized() else 0
+  mine = shard_indices(len(pairs), rank, world)
   rows = []
-  for i in shard_indices(len(pairs), rank, world):
-    xyz0, xyz1 = _cloud(pairs[i][0]), _cloud(pairs[i][1])
-    t = time.perf_counter()
-    T = dgr.register(xyz0, xyz1)
-    info = getattr(dgr, 'last_info', {})
-    rows.append(pack_result(T, info.get('wsum', 0.0), info.get('iterations', 0),
-                            getattr(dgr, 'last_branch', None), 1e3 * (time.perf_counter() - t)))
+  if hasattr(dgr, 'register_batch'):
+    t0 = time.perf_counter()
+    out = dgr.register_batch([(lambda i=i: (_cloud(pairs[i][0]), _cloud(pairs[i][1]))) for i in mine],
+                             inflight=inflight)
+    done = sorted(info.get('t_done', t0) for _, _, info in out)
+    gaps = dict(zip(done, np.diff([t0] + done))) if done else {}
+    for T, branch, info in out:
+      rows.append(pack_result(T, info.get('wsum', 0.0), info.get('iterations', 0), branch,
+                              1e3 * gaps.get(info.get('t_done'), 0.0)))
+  else:
+    for i in mine:
+      xyz0, xyz1 = _cloud(pairs[i][0]), _cloud(pairs[i][1])
+      t = time.perf_counter()
+      T = dgr.register(xyz0, xyz1)
+      info = getattr(dgr, 'last_info', {})
+      rows.append(pack_result(T, info.get('wsum', 0.0), info.get('iterations', 0),
+                              getattr(dgr, 'last_branch', None), 1e3 * (time.perf_counter() - t)))
   return gather_results(rows, len(pairs), device)

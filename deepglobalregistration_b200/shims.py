@@ -40,8 +40,11 @@ def install(force=False):
 
 
 def _open3d_stub():
-  """The part of open3d demo.py:10-48 touches, backed by io.py.  Registration (ICP, RANSAC) is NOT
-  routed through here: DeepGlobalRegistration calls libdgr_b200 for those."""
+  """The part of open3d the reference touches on the registration path: demo.py:10-48 (I/O, PointCloud, a no-op
+  viewer, backed by io.py) and core/deep_global_registration.py:50-64,317-322 + util/pointcloud.py:15-23
+  (pipelines.registration.registration_icp / registration_ransac_based_on_correspondence, utility vectors) backed
+  by libdgr_b200 (o3d_registration.py) - so the reference's OWN DeepGlobalRegistration class and demo.py run on
+  this stack unmodified.  This package's DeepGlobalRegistration does not go through here: it calls the library."""
   import numpy as np
 
   from . import io as dio
@@ -54,6 +57,18 @@ def _open3d_stub():
   o3d.geometry.PointCloud = dio.PointCloud
   o3d.utility = types.ModuleType('open3d.utility')
   o3d.utility.Vector3dVector = lambda a: np.asarray(a, dtype=np.float64).reshape(-1, 3)
+  o3d.utility.Vector2iVector = lambda a: np.asarray(a, dtype=np.int32).reshape(-1, 2)
+  from . import o3d_registration as reg
+  o3d.pipelines = types.ModuleType('open3d.pipelines')
+  o3d.pipelines.registration = types.ModuleType('open3d.pipelines.registration')
+  for name in ('TransformationEstimationPointToPoint', 'ICPConvergenceCriteria', 'RANSACConvergenceCriteria',
+               'CorrespondenceCheckerBasedOnDistance', 'RegistrationResult', 'registration_icp',
+               'registration_ransac_based_on_correspondence'):
+    setattr(o3d.pipelines.registration, name, getattr(reg, name))
+  o3d.registration = o3d.pipelines.registration          # the pre-0.12 module path
+  sys.modules['open3d.pipelines'] = o3d.pipelines
+  sys.modules['open3d.pipelines.registration'] = o3d.pipelines.registration
+  sys.modules['open3d.registration'] = o3d.pipelines.registration
   o3d.utility.VerbosityLevel = types.SimpleNamespace(Error=0, Warning=1, Info=2, Debug=3)
   o3d.utility.set_verbosity_level = lambda level: None
   o3d.visualization = types.ModuleType('open3d.visualization')

@@ -10,7 +10,8 @@
  * Conventions
  *   - plain C, no torch types: raw device pointers + extents; the caller owns every
  *     buffer (inputs, outputs, workspaces); the library never allocates, frees or
- *     retains memory beyond one call;
+ *     retains memory beyond one call (exception: the round-2 executor contexts at the end of this
+ *     header own a device arena);
  *   - every function enqueues its work on `stream` (a cudaStream_t passed as void*)
  *     and returns without synchronising, unless stated otherwise;
  *   - return value 0 = OK, negative = error; dgr_last_error() returns a thread-local
@@ -264,6 +265,142 @@ int32_t dgr_ransac_ws_elems(int64_t n_corr, int64_t num_hyp, int64_t* n_elems);
 int32_t dgr_ransac_correspondence(const float* x, const float* y, const int32_t* idx0, const int32_t* idx1,
                                   int64_t n_corr, double max_dist, int64_t num_hyp, uint64_t seed,
                                   uint64_t* ws, double* result, void* stream);
+
+/* ======================================================================================
+ * Round 2: coordinate planning with device-side counts, and the native executor.
+ * ====================================================================================== */
+
+/* Output-stationary conv1 kernel reading a neighbour table whose rows are nbr_stride apart
+ * (dgr_spconv_table_fwd is the nbr_stride == n_out case). */
+int32_t dgr_spconv_table_fwd_strided(const float* in_feat, int32_t cin, const float* weight, int32_t cout,
+                                     const int32_t* nbr, int32_t K, int64_t n_out, int64_t nbr_stride,
+                                     const float* scale, const float* shift, float* out, void* stream);
+
+/* ---- 3xFP16 mode of the cta_group::2 tensor-core convolution ---------------------------------
+ * fp16 has TF32's 11 significant bits at half the bytes and twice the tensor rate; operands are scaled by
+ * powers of two (exact) so that the tensor's absolute maximum lands in [2^14, 2^15), then split hi / lo as
+ * in the 3xTF32 path: same 2^-21 relative accuracy, 1.5 TF32-MMA equivalents per product instead of 3. */
+/* amax[0] (device float, zeroed by the call) = max |x[i]|. */
+int32_t dgr_absmax_f32(const float* x, int64_t n, float* amax, void* stream);
+int32_t dgr_spconv_tc_f16_supported(int32_t cin, int32_t cout);     /* cin % 64 == 0, cout % 32 == 0, <= 256 */
+/* packed: 4 * K * cin * cout bytes ([K][cin/64][hi|lo][cout][64 halves], shared-memory image order);
+ * scale_ws: device float[2] = (1 / weight scale, max |W|). */
+int32_t dgr_pack_weight_f16(const float* w, int32_t K, int32_t cin, int32_t cout, void* packed, float* scale_ws,
+                            void* stream);
+/* Same contract as dgr_spconv_tc_fwd(cluster = 3) (paired tile list).  amax_in: device float >= max |in_feat|
+ * (dgr_absmax_f32); w_scale: scale_ws of dgr_pack_weight_f16. */
+int32_t dgr_spconv_tc_f16_fwd(const float* in_feat, int32_t cin, const void* weight_h, int32_t cout,
+                              const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,
+                              const int32_t* tile_k, const int32_t* tile_start, int32_t n_tiles, int32_t tile_rows,
+                              const float* amax_in, const float* w_scale, float* out, void* stream);
+
+/* ---- coordinate planning without host round trips (csrc/coordplan.cu) --------------------
+ * Convention: `n_max` is a host-side upper bound of a row count (sizes buffers and grids), `n_dev` a
+ * device int32* holding the actual count (NULL = n_max).  Replaces the MinkowskiEngine coordinate
+ * manager behind ME.SparseTensor / MinkowskiConvolution (core/deep_global_registration.py:167,214,
+ * model/residual_block.py:31-80). */
+/* After dgr_unique_first over the concatenated raw voxel coordinates [n_raw0 + n_raw1, 4] of a scan pair:
+ * coords[i] = raw[sel[i]], xyz[i] = float(point sel[i]) for i < n_unique[0]; counts[4] = (N, N0, N1,
+ * key-overflow flag) with N0 = kept points of cloud 0 (sel ascending: cloud 0 rows first). */
+int32_t dgr_compact_voxel_pair(const int32_t* raw_coords, const int32_t* sel, const int32_t* n_unique,
+                               int64_t n_raw0, int64_t n_raw1, const void* xyz0, int32_t is_f64_0, const void* xyz1,
+                               int32_t is_f64_1, int32_t* coords, float* xyz, int32_t* counts, void* stream);
+/* Table key -> row index of rows known to be distinct (clears the table first). */
+int32_t dgr_table_build_unique(const int32_t* coords, int64_t n_max, const int32_t* n_dev, int32_t ncols,
+                               const dgr_keyspec_t* spec, uint64_t* keys, int32_t* vals, int64_t cap, void* stream);
+/* Coarse maps of `n_levels` (<= 4) tensor strides in one call, all derived from the same fine rows:
+ * level l: coords_out[l][n_max][ncols] (first n_out[l] rows valid, ordered by first occurrence among the
+ * fine rows), table keys[l][cap] / vals[l][cap] (key -> coarse row), n_out[l] device counts.
+ * slot_ws: n_levels * n_max ints; scan_ws: n_levels * dgr_coarse_scan_elems(n_max) ints. */
+int64_t dgr_coarse_scan_elems(int64_t n_max);
+int32_t dgr_coarse_maps(const int32_t* fine, int64_t n_max, const int32_t* n_dev, int32_t ncols,
+                        const dgr_keyspec_t* spec, int32_t n_levels, const int32_t* strides, uint64_t* keys,
+                        int32_t* vals, int64_t cap, int32_t* coords_out, int32_t* n_out, int32_t* slot_ws,
+                        int32_t* scan_ws, void* stream);
+/* Blocked Bloom filter of a table (both bits of a key in one 32-bit word); n_words a power of two. */
+int32_t dgr_bloom2_build(const uint64_t* keys, int64_t cap, uint32_t* words, int64_t n_words, void* stream);
+/* Kernel map, phase 1: bits[K][W] (W = dgr_kmap_mask_words(n_out_max)) holds one bit per (offset, output row),
+ * block_cnt (dgr_kmap_cnt_elems ints) the exclusive-scanned per-(offset, 2048-word block) pair counts,
+ * kofs[K + 2] the bucket offsets + key-overflow flag, meta[5] = (pairs P, 128-row tiles, tiles with an even
+ * count per offset, non-empty offsets, key overflow).  bloom_words (optional, <= 32768 words) is copied to
+ * shared memory and answers most misses there.  No host synchronisation. */
+int64_t dgr_kmap_mask_words(int64_t n_out_max);
+int64_t dgr_kmap_cnt_elems(int32_t K, int64_t n_out_max);
+int32_t dgr_kmap_probe(const int32_t* out_coords, int64_t n_out_max, const int32_t* n_out_dev, int32_t ncols,
+                       const dgr_keyspec_t* spec, const uint64_t* in_keys, const int32_t* in_vals, int64_t in_cap,
+                       const uint32_t* bloom_words, int64_t n_bloom_words, const int32_t* offsets, int32_t K,
+                       uint32_t* bits, int32_t* block_cnt, int32_t* kofs, int32_t* meta, void* stream);
+/* Kernel map, phase 2 (after the caller has read P from meta): in_idx[P], out_idx[P] sorted by (kappa, j),
+ * bit-identical to dgr_kernel_map_fill. */
+int32_t dgr_kmap_fill(const uint32_t* bits, const int32_t* block_cnt, int32_t K, int64_t n_out_max,
+                      const int32_t* out_coords, int32_t ncols, const dgr_keyspec_t* spec, const uint64_t* in_keys,
+                      const int32_t* in_vals, int64_t in_cap, const int32_t* offsets, int32_t* in_idx,
+                      int32_t* out_idx, void* stream);
+/* Dense neighbour table nbr[kappa * nbr_stride + j] (-1 = no neighbour) with a device-side row count. */
+int32_t dgr_kmap_dense(const int32_t* out_coords, int64_t n_out_max, const int32_t* n_out_dev, int32_t ncols,
+                       const dgr_keyspec_t* spec, const uint64_t* in_keys, const int32_t* in_vals, int64_t in_cap,
+                       const int32_t* offsets, int32_t K, int32_t* nbr, int64_t nbr_stride, void* stream);
+
+/* ---- native executor (csrc/exec.cu) ------------------------------------------------------
+ * A context owns a stream (or uses the one given), a grow-only device arena and pinned staging; calls
+ * on one context are serialised by the caller, different contexts may be driven from different host
+ * threads (two pairs in flight per GPU).  Unlike the operator-level entry points above, these allocate
+ * device memory internally (the arena) and synchronise the context's stream where stated. */
+typedef struct dgr_ctx dgr_ctx_t;
+typedef struct dgr_net dgr_net_t;
+int32_t dgr_ctx_create(int32_t device, void* stream /* NULL: own non-blocking stream */, dgr_ctx_t** out);
+int32_t dgr_ctx_destroy(dgr_ctx_t* ctx);
+void* dgr_ctx_stream(dgr_ctx_t* ctx);
+/* stats[6]: host reads, device-to-host bytes, host-to-device bytes of the last call; arena high-water mark
+ * [bytes], cudaMalloc calls of the arena so far, arena chunks. */
+int32_t dgr_ctx_stats(dgr_ctx_t* ctx, int64_t* stats);
+/* Per-launch CUDA-event timing of the convolution launches (bench.py's live roofline):
+ * dgr_ctx_profile(ctx, 1) starts recording, dgr_ctx_profile_read synchronises and returns rows of
+ * (milliseconds, algorithmic flops, gather-scatter-model bytes, kind: 0 tensor-core / 1 fp32 / 2 table). */
+int32_t dgr_ctx_profile(dgr_ctx_t* ctx, int32_t enable);
+int64_t dgr_ctx_profile_read(dgr_ctx_t* ctx, double* rows, int64_t max_rows);
+/* Stage times [ms] of the last dgr_pair_register with profiling on (CUDA events on the context's stream):
+ * upload + voxelisation, FCGF coordinate phase, host read 1 + FCGF pair lists, FCGF convolutions, feature kNN,
+ * 6-D coordinate phase, host read 2 + 6-D pair lists, inlier convolutions, weights + Procrustes + refinement
+ * (+ ICP).  Returns the number of stages written. */
+int32_t dgr_ctx_stage_times(dgr_ctx_t* ctx, double* ms, int32_t max_stages);
+
+/* A ResUNet2-family network (model/resunet.py:419-665) from 66 DEVICE parameter pointers in execution order:
+ *   for l = 1..4:   conv{l}.kernel, norm{l} scale, shift, block{l}.conv1.kernel, block{l}.norm1 scale, shift,
+ *                   block{l}.conv2.kernel, block{l}.norm2 scale, shift
+ *   for l = 4,3,2:  conv{l}_tr.kernel, norm{l}_tr scale, shift, block{l}_tr.conv1.kernel, ... (same 9)
+ *   conv1_tr.kernel, final.kernel, final.bias
+ * kernels in ME layout [K, cin, cout]; scale / shift = eval-mode BatchNorm folded (model/common.py:13).
+ * channels / tr_channels: CHANNELS / TR_CHANNELS of the model class (5 ints each, index 0 unused).  The
+ * parameters must outlive the network; the TF32 weight slabs are packed here, once. */
+int32_t dgr_net_create(int32_t device, int32_t D, int32_t in_ch, int32_t out_ch, int32_t conv1_ks, int32_t normalize,
+                       const int32_t* channels, const int32_t* tr_channels, const float* const* params,
+                       int32_t n_params, void* stream, dgr_net_t** out);
+int32_t dgr_net_destroy(dgr_net_t* net);
+/* Forward pass (model/resunet.py:598-649) of one sparse tensor: coords [n, D+1] int32 (distinct rows),
+ * feats [n, in_ch] (NULL = ones), out [n, out_ch]; device pointers.  Resets the context's arena, ONE host
+ * read inside, returns with the convolution phase enqueued on the context's stream. */
+int32_t dgr_net_forward(dgr_ctx_t* ctx, dgr_net_t* net, const int32_t* coords, int64_t n, const float* feats,
+                        float* out);
+
+/* DeepGlobalRegistration.register() (core/deep_global_registration.py:238-324) for inlier_feature_type 'ones':
+ * xyz0 / xyz1 = raw points [n, 3] (float64 or float32; host pointers when on_host, else device pointers).
+ * Three host reads.  result (host double[64]):
+ *   [0..16)  R (9, row-major), t (3), refinement iterations, final loss, break count, active correspondences
+ *   [16]     weight sum (the gate of :276-281 and the safeguard call are the caller's: dgr_pair_safeguard)
+ *   [17..37) ICP (use_icp): 4x4 pose, fitness, inlier RMSE, iterations, correspondences
+ *   [40..44) N0, N1 (voxels per cloud), host reads, device-to-host bytes */
+int32_t dgr_pair_register(dgr_ctx_t* ctx, dgr_net_t* fcgf, dgr_net_t* inlier, const void* xyz0, int64_t n_raw0,
+                          int32_t is_f64_0, const void* xyz1, int64_t n_raw1, int32_t is_f64_1, int32_t on_host,
+                          double voxel, float clip, int32_t use_icp, double* result);
+/* Safeguard branch (:302-315) on the pair this context registered last: RANSAC over its correspondences, then
+ * (use_icp) ICP from that pose.  result (host double[40]): RANSAC 20 doubles, ICP 20 doubles. */
+int32_t dgr_pair_safeguard(dgr_ctx_t* ctx, double max_dist, int64_t num_hyp, uint64_t seed, int32_t use_icp,
+                           double* result);
+/* Intermediate tensors of the last pair: which = 0 coords [N, 4] i32, 1 xyz [N, 3] f32, 2 FCGF features
+ * [N, C] f32, 3 idx1 [N0] i32, 4 6-D coords [N0, 7] i32, 5 logits [N0] f32, 6 weights [N0] f32, 7 sel [N] i32.
+ * dst NULL: shape only; else a synchronous copy into the DEVICE buffer dst. */
+int32_t dgr_pair_tap(dgr_ctx_t* ctx, int32_t which, int64_t* rows, int32_t* cols, void* dst);
 
 #ifdef __cplusplus
 }
