@@ -77,7 +77,10 @@ SIGNATURES = {
     'dgr_kmap_cnt_elems': [_i32, _i64],
     'dgr_kmap_probe': [_p, _i64, _p, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p],
     'dgr_kmap_fill': [_p, _p, _i32, _i64, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p],
-    'dgr_kmap_dense': [_p, _i64, _p, _i32, _p, _p, _p, _i64, _p, _i32, _p, _i64, _p],
+    'dgr_kmap_dense': [_p, _i64, _p, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _p, _p],
+    'dgr_spconv_os_supported': [_i32, _i32],
+    'dgr_spconv_os_fwd': [_p, _i32, _p, _i32, _p, _i64, _i32, _i64, _p, _p, _p, _i32, _p, _p],
+    'dgr_spconv_wgrad': [_p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _p],
     'dgr_absmax_f32': [_p, _i64, _p, _p],
     'dgr_spconv_tc_f16_supported': [_i32, _i32],
     'dgr_pack_weight_f16': [_p, _i32, _i32, _i32, _p, _p, _p],
@@ -427,6 +430,16 @@ def spconv_fwd(feat, weight, km, out, relu_in=False):
   return out
 
 
+def spconv_wgrad(feat, grad_out, km):
+  """Weight gradient [K, cin, cout] of the convolution over `km` (training)."""
+  _chk(feat, torch.float32, 'feat'); _chk(grad_out, torch.float32, 'grad_out')
+  cin, cout = feat.shape[1], grad_out.shape[1]
+  dw = torch.empty(km.K, cin, cout, dtype=torch.float32, device=feat.device)
+  call('dgr_spconv_wgrad', ptr(feat), cin, ptr(grad_out), cout, ptr(km.in_idx), ptr(km.out_idx), ptr(km.kofs), km.K,
+       ptr(dw), stream())
+  return dw
+
+
 def tc_supported(cin, cout):
   return bool(lib().dgr_spconv_tc_supported(int(cin), int(cout)))
 
@@ -503,6 +516,16 @@ def spconv_tc_f16_fwd(feat, weight, km, out, amax=None):
   tk, ts, nt = km.paired_tiles()
   call('dgr_spconv_tc_f16_fwd', ptr(feat), cin, ptr(packed), cout, ptr(km.in_idx), ptr(km.out_idx), ptr(km.kofs),
        ptr(tk), ptr(ts), nt, TILE_ROWS, ptr(amax), ptr(wscale), ptr(out), stream())
+  return out
+
+
+def spconv_os_fwd(feat, weight_t, nbr, cout, scale=None, shift=None, residual=None, relu=False):
+  """Output-stationary tensor-core convolution with the fused epilogue; nbr: dense table [K, n_out] int32."""
+  _chk(feat, torch.float32, 'feat'); _chk(weight_t, torch.float32, 'weight_t'); _chk(nbr, torch.int32, 'nbr')
+  K, n_out = nbr.shape
+  out = torch.empty(n_out, cout, dtype=torch.float32, device=feat.device)
+  call('dgr_spconv_os_fwd', ptr(feat), feat.shape[1], ptr(weight_t), cout, ptr(nbr), nbr.stride(0), K, n_out,
+       ptr(scale), ptr(shift), ptr(residual), int(relu), ptr(out), stream())
   return out
 
 

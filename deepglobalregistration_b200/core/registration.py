@@ -33,6 +33,26 @@ def weighted_procrustes(X, Y, w, eps=F32_EPS):
   return res[:9].reshape(3, 3).clone(), res[9:12].clone()
 
 
+def weighted_procrustes_autograd(X, Y, w, eps=F32_EPS):
+  """Differentiable weighted Procrustes for training (core/registration.py:91-113 as called from
+  core/trainer.py:580-600): the same arithmetic in torch ops on the inputs' device - fp32 moments, the 3x3 SVD in
+  float64 with the det(U) det(V) reflection fix - so gradients reach the weights through torch's SVD backward.
+  -> (R [3,3], t [3]) on the inputs' device.  Inference uses weighted_procrustes (the cluster kernel)."""
+  X, Y = X.float(), Y.float()
+  w = w.reshape(-1, 1).float()
+  wn = w / (w.abs().sum() + eps)
+  mx = (wn * X).sum(0, keepdim=True)
+  my = (wn * Y).sum(0, keepdim=True)
+  S = ((Y - my).t() @ (wn * (X - mx))).double()
+  U, _, Vh = torch.linalg.svd(S)
+  d = torch.ones(3, dtype=torch.float64, device=S.device)
+  if float(torch.det(U) * torch.det(Vh)) < 0:
+    d = d * torch.tensor([1.0, 1.0, -1.0], dtype=torch.float64, device=S.device)
+  R = (U @ torch.diag(d) @ Vh).float()
+  t = my.reshape(3) - (R @ mx.reshape(3, 1)).reshape(3)
+  return R, t
+
+
 def GlobalRegistration(points, trans_points, weights=None, max_iter=1000, verbose=False, stat_freq=20,
                        max_break_count=20, break_threshold_ratio=1e-5, loss_fn=None, quantization_size=1):
   """-> (R [3,3], t [1,3], dict(iterations, loss, break_count)); tensors on the input device."""

@@ -21,22 +21,22 @@ void dgr_note_launches(int n);   // bookkeeping for dgr_launch_count()
 
 #define DGR_LAUNCH_CHECK() DGR_CUDA_CHECK(cudaGetLastError())
 
-// Opt a kernel in to large dynamic shared memory - ONCE per call site, to the device maximum (227 KB on
-// sm_100), whatever this launch needs: the attribute is per function, not per launch, so two host threads
-// (two pairs in flight) that set launch-specific sizes would race (thread A sets 100 KB, thread B sets 60 KB,
-// A's launch then fails with "invalid argument").  Setting the same maximum twice is harmless.
-#define DGR_SMEM_OPTIN_MAX 232448
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is per FUNCTION, not per launch, and only
+// ever raised here (monotone maximum per call site, under a mutex): two host threads - two pairs in flight -
+// that set launch-specific sizes without this would race (thread A sets 100 KB, thread B sets 60 KB, A's launch
+// then fails with "invalid argument").  cudaFuncSetAttribute is a driver call that takes the context lock, so
+// it is skipped once the attribute is large enough.
+#include <mutex>
 #define DGR_ENSURE_SMEM(func, bytes)                                                                 \
   do {                                                                                               \
-    static std::atomic<int> done_smem_{0};                                                           \
-    if ((size_t)(bytes) > (size_t)DGR_SMEM_OPTIN_MAX) {                                              \
-      dgr_set_error("%s:%d: %zu bytes of shared memory requested", __FILE__, __LINE__, (size_t)(bytes)); \
-      return DGR_ERR_ARG;                                                                            \
-    }                                                                                                \
-    if ((size_t)(bytes) > 48 * 1024 && !done_smem_.load(std::memory_order_acquire)) {                \
-      DGR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                          DGR_SMEM_OPTIN_MAX));                                      \
-      done_smem_.store(1, std::memory_order_release);                                                \
+    static std::atomic<int> cur_smem_{0};                                                            \
+    static std::mutex smem_mu_;                                                                      \
+    if ((int)(bytes) > cur_smem_.load(std::memory_order_acquire)) {                                  \
+      std::lock_guard<std::mutex> lock_(smem_mu_);                                                   \
+      if ((int)(bytes) > cur_smem_.load(std::memory_order_relaxed)) {                                \
+        DGR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+        cur_smem_.store((int)(bytes), std::memory_order_release);                                    \
+      }                                                                                              \
     }                                                                                                \
   } while (0)
 
@@ -90,10 +90,12 @@ __device__ __forceinline__ uint32_t dgr_hash_insert(uint64_t* keys, uint64_t mas
 __device__ __forceinline__ int32_t dgr_hash_lookup(const uint64_t* __restrict__ keys,
                                                    const int32_t* __restrict__ vals, uint64_t mask,
                                                    uint64_t key) {
+  // ld.global.cg (L2, coherent): random 8-byte probes gain nothing from L1, and a table is written by the
+  // kernels launched just before its readers - no reliance on the non-coherent path being flushed in between
   uint64_t s = dgr_mix64(key) & mask;
   while (true) {
-    uint64_t k = __ldg(keys + s);
-    if (k == key) return __ldg(vals + s);
+    uint64_t k = __ldcg(reinterpret_cast<const unsigned long long*>(keys) + s);
+    if (k == key) return __ldcg(vals + s);
     if (k == DGR_EMPTY_KEY) return -1;
     s = (s + 1) & mask;
   }

@@ -266,67 +266,140 @@ __global__ void bloom2_build_kernel(const uint64_t* __restrict__ keys, int64_t c
 // ---------------------------------------------------------------------------------------
 // kernel maps: probe -> bit masks + block counts, scan, fill
 // ---------------------------------------------------------------------------------------
-// grid (row blocks of 512 rows, kappa chunks); mask[kappa * W + w] = ballot of warp w's 32 rows
-template <bool kBloom>
+// Probe kernel.  grid (row blocks of 512 rows, kappa chunks); thread = output row.
+//
+// Two phases per warp, decoupled by a shared-memory queue:
+//   generate  every lane tests its row's neighbour key against the Bloom filter (shared memory, no global
+//             traffic); lanes whose key MAY exist push (kappa, lane) into the warp's queue;
+//   drain     whenever 32 candidates are queued, every lane takes ONE and does the hash-table lookup (L2):
+//             all 32 lanes busy, 32 independent L2 chains in flight.
+// Probing in place instead would make the whole warp wait for an L2 round trip whenever ANY of its 32 lanes
+// passes the filter (a 3 % pass rate per lane is 62 % per warp) with one or two lanes doing useful work.
+// Output: kDense ? nbr[kappa * nbr_stride + j] = input row or -1
+//                : bits[kappa * W + w] = ballot of warp w's rows (+ per-(kappa, 2048-word block) counts)
+template <bool kBloom, bool kDense>
 __global__ void __launch_bounds__(kProbeThreads, 2)
 kmap_probe_kernel(const int32_t* __restrict__ out_coords, const int32_t* __restrict__ n_out_dev, int64_t n_out_max,
                   int ncols, const dgr_keyspec_t* __restrict__ spec_p, const uint64_t* __restrict__ keys,
                   const int32_t* __restrict__ vals, uint64_t mask, const uint32_t* __restrict__ bloom,
                   uint32_t n_bloom_words, const int32_t* __restrict__ offsets, int K, int k_per_block,
-                  uint32_t* __restrict__ bits, int W, int32_t* block_cnt, int bpk) {
+                  uint32_t* __restrict__ bits, int W, int32_t* block_cnt, int bpk, int32_t* __restrict__ nbr,
+                  int64_t nbr_stride, int32_t* hit_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  long long* delta = reinterpret_cast<long long*>(smem_raw);                          // [k_per_block]
-  uint32_t* bloom_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)k_per_block * 8);   // [n_bloom_words]
+  constexpr int kWarps = kProbeThreads / 32;
+  long long* delta = reinterpret_cast<long long*>(smem_raw);                               // [k_per_block]
+  uint32_t* mtile = reinterpret_cast<uint32_t*>(smem_raw + (size_t)k_per_block * 8);       // [kWarps][k_per_block]
+  uint16_t* queue = reinterpret_cast<uint16_t*>(mtile + (size_t)kWarps * k_per_block);     // [kWarps][64]
+  uint32_t* bloom_s = reinterpret_cast<uint32_t*>(queue + kWarps * 64);                    // [n_bloom_words]
   const int n_out = dev_count(n_out_dev, n_out_max);
+  const int k0 = blockIdx.y * k_per_block;
+  const int kn = min(k_per_block, K - k0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if ((int64_t)blockIdx.x * kProbeThreads >= n_out) {
-    // rows beyond the actual count: their mask words must still read as zero
-    const int k0 = blockIdx.y * k_per_block, kn = min(k_per_block, K - k0);
-    const int w = blockIdx.x * (kProbeThreads / 32) + (threadIdx.x >> 5);
-    if ((threadIdx.x & 31) == 0 && w < W)
-      for (int kk = 0; kk < kn; ++kk) bits[(int64_t)(k0 + kk) * W + w] = 0u;
+    // rows beyond the actual count: their mask words must still read as zero (a dense table is never read there)
+    if (!kDense) {
+      const int w = blockIdx.x * kWarps + warp;
+      if (lane == 0 && w < W)
+        for (int kk = 0; kk < kn; ++kk) bits[(int64_t)(k0 + kk) * W + w] = 0u;
+    }
     return;
   }
   const dgr_keyspec_t s = *spec_p;
-  const int k0 = blockIdx.y * k_per_block;
-  const int kn = min(k_per_block, K - k0);
   for (int kk = threadIdx.x; kk < kn; kk += blockDim.x) {
     long long d = 0;
     const int32_t* o = offsets + (int64_t)(k0 + kk) * (ncols - 1);
     for (int a = 0; a < ncols - 1; ++a) d += (long long)o[a] * (1ll << s.shift[a + 1]);
     delta[kk] = d;
   }
+  if (!kDense)
+    for (int e = threadIdx.x; e < kWarps * k_per_block; e += blockDim.x) mtile[e] = 0u;
   if (kBloom)
     for (uint32_t i = threadIdx.x; i < n_bloom_words; i += blockDim.x) bloom_s[i] = bloom[i];
   __syncthreads();
   const int64_t j = (int64_t)blockIdx.x * kProbeThreads + threadIdx.x;
   const bool live = j < n_out;
   const uint64_t key = live ? dgr_pack_key(out_coords + j * ncols, s) : 0;
-  const int lane = threadIdx.x & 31;
-  const int w = (int)(j >> 5);
+  const uint32_t key_lo = (uint32_t)key, key_hi = (uint32_t)(key >> 32);
+  const int64_t row0 = j - lane;                       // first row of this warp
   const uint32_t wm = n_bloom_words - 1;
-  const int cnt_col = w / kScanElems;
-  for (int kk = 0; kk < kn; kk += 4) {
-    uint64_t q[4];
-    bool maybe[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      q[u] = key + (uint64_t)delta[min(kk + u, kn - 1)];
-      if (kBloom) {
-        const uint32_t h = bloom_mix(q[u]);
-        const uint32_t b = bloom_bits(h);
-        maybe[u] = (bloom_s[h & wm] & b) == b;
-      } else {
-        maybe[u] = true;
+  uint16_t* q = queue + warp * 64;
+  uint32_t* mt = mtile + warp * k_per_block;
+  int qn = 0;                                          // queued candidates (warp-uniform)
+
+  auto drain = [&](int count) {                        // lanes < count take one candidate each
+    __syncwarp();
+    const uint32_t e = lane < count ? q[lane] : 0u;
+    const int src = e & 31, kq = e >> 5;
+    const uint32_t lo = __shfl_sync(0xffffffffu, key_lo, src), hi = __shfl_sync(0xffffffffu, key_hi, src);
+    if (lane < count) {
+      const uint64_t qq = (((uint64_t)hi << 32) | lo) + (uint64_t)delta[kq];
+      const int32_t i = dgr_hash_lookup(keys, vals, mask, qq);
+      if (kDense) {
+        nbr[(int64_t)(k0 + kq) * nbr_stride + row0 + src] = i;
+        if (hit_count != nullptr) {
+          const uint32_t act = __activemask();
+          const uint32_t hits = __ballot_sync(act, i >= 0);
+          if (lane == (__ffs(act) - 1) && hits) atomicAdd(hit_count, __popc(hits));
+        }
+      } else if (i >= 0) {
+        atomicOr(mt + kq, 1u << src);
       }
     }
+    __syncwarp();
+    // move the (at most 31) entries behind the drained ones to the front
+    const uint32_t rest = (lane + 32 < qn) ? q[lane + 32] : 0u;
+    __syncwarp();
+    if (lane + 32 < qn) q[lane] = (uint16_t)rest;
+    qn = qn > 32 ? qn - 32 : 0;
+    __syncwarp();
+  };
+
+  if (!kBloom && !kDense) {
+    // no filter (3^3 kernels: ~60 % of the probes hit): probe in place, four independent lookups in flight
+    const int w = (int)(j >> 5);
+    const int cnt_col = w / kScanElems;
+    for (int kk = 0; kk < kn; kk += 4) {
+      bool found[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (kk + u >= kn) break;                                        // uniform
-      const bool found = live && maybe[u] && dgr_hash_lookup(keys, vals, mask, q[u]) >= 0;
-      const uint32_t m = __ballot_sync(0xffffffffu, found);
-      if (lane == 0 && w < W) {       // the last row block may hold warps past the last mask word
-        bits[(int64_t)(k0 + kk + u) * W + w] = m;
-        if (m) atomicAdd(block_cnt + (int64_t)(k0 + kk + u) * bpk + cnt_col, __popc(m));
+      for (int u = 0; u < 4; ++u)
+        found[u] = live && kk + u < kn && dgr_hash_lookup(keys, vals, mask, key + (uint64_t)delta[min(kk + u, kn - 1)]) >= 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kk + u >= kn) break;                                     // uniform
+        const uint32_t m = __ballot_sync(0xffffffffu, found[u]);
+        if (lane == 0 && w < W) {
+          bits[(int64_t)(k0 + kk + u) * W + w] = m;
+          if (m) atomicAdd(block_cnt + (int64_t)(k0 + kk + u) * bpk + cnt_col, __popc(m));
+        }
+      }
+    }
+    return;
+  }
+  for (int kk = 0; kk < kn; ++kk) {
+    bool maybe = live;
+    if (kBloom && live) {
+      const uint32_t h = bloom_mix(key + (uint64_t)delta[kk]);
+      const uint32_t b = bloom_bits(h);
+      maybe = (bloom_s[h & wm] & b) == b;
+    }
+    if (kDense && live && !maybe) nbr[(int64_t)(k0 + kk) * nbr_stride + j] = -1;
+    const uint32_t cand = __ballot_sync(0xffffffffu, maybe);
+    if (cand) {
+      if (maybe) q[qn + __popc(cand & ((1u << lane) - 1u))] = (uint16_t)((kk << 5) | lane);
+      qn += __popc(cand);
+      if (qn >= 32) drain(32);
+    }
+  }
+  if (qn > 0) drain(qn);
+  if (!kDense) {
+    __syncwarp();
+    const int w = (int)(j >> 5);
+    if (w < W) {
+      const int cnt_col = w / kScanElems;
+      for (int kk = lane; kk < kn; kk += 32) {
+        const uint32_t m = mt[kk];
+        bits[(int64_t)(k0 + kk) * W + w] = m;
+        if (m) atomicAdd(block_cnt + (int64_t)(k0 + kk) * bpk + cnt_col, __popc(m));
       }
     }
   }
@@ -375,76 +448,61 @@ __global__ void kmap_scan_kernel(int32_t* cnt, int K, int bpk, int tile_rows, in
   }
 }
 
-// grid (bpk, K): block (b, kappa) owns mask words [b * 2048, ...) of bucket kappa
-__global__ void kmap_fill_kernel(const uint32_t* __restrict__ bits, int W, const int32_t* __restrict__ block_ofs,
-                                 const int32_t* __restrict__ out_coords, int ncols,
-                                 const dgr_keyspec_t* __restrict__ spec_p, const uint64_t* __restrict__ keys,
-                                 const int32_t* __restrict__ vals, uint64_t mask,
-                                 const int32_t* __restrict__ offsets, int32_t* __restrict__ in_idx,
-                                 int32_t* __restrict__ out_idx) {
+// Fill: grid (8 * bpk, K); block (x, kappa) owns the 256 mask words [x * 256, +256) of bucket kappa, one per
+// thread.  A word's 32 hits are resolved by the 32 LANES of a warp in parallel (each lane: one hash lookup,
+// consecutive output positions), so the longest serial chain is the 32 words of a warp, not the hits of a
+// thread.  Offsets: the scanned count of the enclosing 2048-word block, plus the set bits of the 256-word
+// sub-blocks before this one, plus the in-block exclusive scan.
+__global__ void __launch_bounds__(kThreads)
+kmap_fill_kernel(const uint32_t* __restrict__ bits, int W, int bpk, const int32_t* __restrict__ block_ofs,
+                 const int32_t* __restrict__ out_coords, int ncols, const dgr_keyspec_t* __restrict__ spec_p,
+                 const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals, uint64_t mask,
+                 const int32_t* __restrict__ offsets, int32_t* __restrict__ in_idx, int32_t* __restrict__ out_idx) {
+  __shared__ uint32_t s_mask[kThreads];
+  __shared__ int s_base[kThreads];
+  __shared__ int s_red[kThreads / 32];
   const int kappa = blockIdx.y;
-  const int w0 = blockIdx.x * kScanElems + threadIdx.x * 8;
-  uint32_t m[8];
-  int c = 0;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    m[e] = (w0 + e < W) ? bits[(int64_t)kappa * W + w0 + e] : 0u;
-    c += __popc(m[e]);
+  const int sub = blockIdx.x & 7, grp = blockIdx.x >> 3;       // 8 sub-blocks of 256 words per 2048-word block
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t row_base = (int64_t)kappa * W;
+  const int w_grp = grp * kScanElems;
+  // set bits of this group's sub-blocks before `sub`
+  int before = 0;
+  for (int q = 0; q < sub; ++q) {
+    const int w = w_grp + q * kThreads + t;
+    if (w < W) before += __popc(bits[row_base + w]);
   }
-  int pos = block_ofs[(int64_t)kappa * gridDim.x + blockIdx.x] + dgr_block_exclusive_scan_256(c, nullptr);
-  if (c == 0) return;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+  if (lane == 0) s_red[warp] = before;
+  const int w_own = w_grp + sub * kThreads + t;
+  const uint32_t m_own = w_own < W ? bits[row_base + w_own] : 0u;
+  __syncthreads();
+  int prior = 0;
+#pragma unroll
+  for (int k = 0; k < kThreads / 32; ++k) prior += s_red[k];
+  __syncthreads();
+  int total = 0;
+  const int excl = dgr_block_exclusive_scan_256(__popc(m_own), &total);
+  if (total == 0) return;                                      // uniform
+  s_mask[t] = m_own;
+  s_base[t] = block_ofs[(int64_t)kappa * bpk + grp] + prior + excl;
+  __syncthreads();
   const dgr_keyspec_t s = *spec_p;
   long long d = 0;
   const int32_t* o = offsets + (int64_t)kappa * (ncols - 1);
   for (int a = 0; a < ncols - 1; ++a) d += (long long)o[a] * (1ll << s.shift[a + 1]);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    uint32_t mm = m[e];
-    while (mm) {
-      const int b = __ffs(mm) - 1;
-      mm &= mm - 1;
-      const int64_t j = (int64_t)(w0 + e) * 32 + b;
-      const uint64_t q = dgr_pack_key(out_coords + j * ncols, s) + (uint64_t)d;
-      in_idx[pos] = dgr_hash_lookup(keys, vals, mask, q);
+  const int w_first = w_grp + sub * kThreads + warp * 32;      // this warp resolves its own 32 words
+  for (int u = 0; u < 32; ++u) {
+    const uint32_t m = s_mask[warp * 32 + u];
+    if (m == 0u) continue;                                     // uniform
+    if ((m >> lane) & 1u) {
+      const int64_t j = (int64_t)(w_first + u) * 32 + lane;
+      const int pos = s_base[warp * 32 + u] + __popc(m & ((1u << lane) - 1u));
+      const uint64_t qq = dgr_pack_key(out_coords + j * ncols, s) + (uint64_t)d;
+      in_idx[pos] = dgr_hash_lookup(keys, vals, mask, qq);
       out_idx[pos] = (int32_t)j;
-      ++pos;
     }
-  }
-}
-
-// dense neighbour table (conv1 of the 3-D network: read by the output-stationary kernel) with a
-// device-side row count and an explicit row stride
-__global__ void kmap_dense_kernel(const int32_t* __restrict__ out_coords, const int32_t* __restrict__ n_out_dev,
-                                  int64_t n_out_max, int ncols, const dgr_keyspec_t* __restrict__ spec_p,
-                                  const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
-                                  uint64_t mask, const int32_t* __restrict__ offsets, int K, int k_per_block,
-                                  int32_t* __restrict__ nbr, int64_t nbr_stride) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  long long* delta = reinterpret_cast<long long*>(smem_raw);
-  const int n_out = dev_count(n_out_dev, n_out_max);
-  if ((int64_t)blockIdx.x * blockDim.x >= n_out) return;
-  const dgr_keyspec_t s = *spec_p;
-  const int k0 = blockIdx.y * k_per_block;
-  const int kn = min(k_per_block, K - k0);
-  for (int kk = threadIdx.x; kk < kn; kk += blockDim.x) {
-    long long d = 0;
-    const int32_t* o = offsets + (int64_t)(k0 + kk) * (ncols - 1);
-    for (int a = 0; a < ncols - 1; ++a) d += (long long)o[a] * (1ll << s.shift[a + 1]);
-    delta[kk] = d;
-  }
-  __syncthreads();
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_out) return;
-  const uint64_t key = dgr_pack_key(out_coords + j * ncols, s);
-  int32_t* dst = nbr + (int64_t)k0 * nbr_stride + j;
-  for (int kk = 0; kk < kn; kk += 4) {
-    int32_t f[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      f[u] = (kk + u < kn) ? dgr_hash_lookup(keys, vals, mask, key + (uint64_t)delta[kk + u]) : -1;
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (kk + u < kn) dst[(int64_t)(kk + u) * nbr_stride] = f[u];
   }
 }
 
@@ -549,6 +607,18 @@ int64_t dgr_kmap_cnt_elems(int32_t K, int64_t n_out_max) {
   return (int64_t)K * ((W + kScanElems - 1) / kScanElems) + 2;
 }
 
+static size_t probe_smem_bytes(int k_per_block, int64_t n_bloom_words) {
+  return (size_t)k_per_block * 8 + (size_t)(kProbeThreads / 32) * k_per_block * 4 + (size_t)(kProbeThreads / 32) * 64 * 2 +
+         (size_t)n_bloom_words * 4;
+}
+static int probe_k_per_block(int K, unsigned row_blocks) {
+  // kappa chunks: enough blocks for ~2 waves of the 148 SMs at 2 blocks per SM, at most 96 offsets per block
+  int k_per_block = K;
+  while (k_per_block > 16 && (int64_t)row_blocks * ((K + k_per_block - 1) / k_per_block) < 592) k_per_block = (k_per_block + 1) / 2;
+  if (k_per_block > 96) k_per_block = 96;
+  return (k_per_block + 3) & ~3;
+}
+
 int32_t dgr_kmap_probe(const int32_t* out_coords, int64_t n_out_max, const int32_t* n_out_dev, int32_t ncols,
                        const dgr_keyspec_t* spec, const uint64_t* in_keys, const int32_t* in_vals, int64_t in_cap,
                        const uint32_t* bloom_words, int64_t n_bloom_words, const int32_t* offsets, int32_t K,
@@ -563,25 +633,20 @@ int32_t dgr_kmap_probe(const int32_t* out_coords, int64_t n_out_max, const int32
   const int W = (int)dgr_kmap_mask_words(nmx);
   const int bpk = (W + kScanElems - 1) / kScanElems;
   DGR_CUDA_CHECK(cudaMemsetAsync(block_cnt, 0, (size_t)dgr_kmap_cnt_elems(K, nmx) * sizeof(int32_t), st));
-  // kappa chunks: enough blocks for ~2 waves of the 148 SMs at 2 blocks per SM, at most 128 offsets per block
   const unsigned row_blocks = dgr_blocks(nmx, kProbeThreads);
-  int k_per_block = K;
-  while (k_per_block > 16 && (int64_t)row_blocks * ((K + k_per_block - 1) / k_per_block) < 592) k_per_block = (k_per_block + 1) / 2;
-  if (k_per_block > 128) k_per_block = 128;
-  k_per_block = (k_per_block + 3) & ~3;
+  const int k_per_block = probe_k_per_block(K, row_blocks);
   const dim3 grid(row_blocks, (K + k_per_block - 1) / k_per_block);
   if (bloom_words != nullptr) {
-    const size_t smem = (size_t)k_per_block * 8 + (size_t)n_bloom_words * 4;
-    DGR_ENSURE_SMEM(kmap_probe_kernel<true>, smem);
-    kmap_probe_kernel<true><<<grid, kProbeThreads, smem, st>>>(out_coords, n_out_dev, n_out_max, ncols, spec, in_keys,
-                                                               in_vals, (uint64_t)in_cap - 1, bloom_words,
-                                                               (uint32_t)n_bloom_words, offsets, K, k_per_block, bits,
-                                                               W, block_cnt, bpk);
+    const size_t smem = probe_smem_bytes(k_per_block, n_bloom_words);
+    DGR_ENSURE_SMEM((kmap_probe_kernel<true, false>), smem);
+    kmap_probe_kernel<true, false><<<grid, kProbeThreads, smem, st>>>(
+        out_coords, n_out_dev, n_out_max, ncols, spec, in_keys, in_vals, (uint64_t)in_cap - 1, bloom_words,
+        (uint32_t)n_bloom_words, offsets, K, k_per_block, bits, W, block_cnt, bpk, nullptr, 0, nullptr);
   } else {
-    const size_t smem = (size_t)k_per_block * 8;
-    kmap_probe_kernel<false><<<grid, kProbeThreads, smem, st>>>(out_coords, n_out_dev, n_out_max, ncols, spec, in_keys,
-                                                                in_vals, (uint64_t)in_cap - 1, nullptr, 1u, offsets, K,
-                                                                k_per_block, bits, W, block_cnt, bpk);
+    const size_t smem = probe_smem_bytes(k_per_block, 0);
+    kmap_probe_kernel<false, false><<<grid, kProbeThreads, smem, st>>>(
+        out_coords, n_out_dev, n_out_max, ncols, spec, in_keys, in_vals, (uint64_t)in_cap - 1, nullptr, 1u, offsets, K,
+        k_per_block, bits, W, block_cnt, bpk, nullptr, 0, nullptr);
   }
   kmap_scan_kernel<<<1, 1024, 0, st>>>(block_cnt, K, bpk, 128, kofs, meta, spec);
   dgr_note_launches(2);
@@ -596,9 +661,9 @@ int32_t dgr_kmap_fill(const uint32_t* bits, const int32_t* block_cnt, int32_t K,
   const int64_t nmx = n_out_max > 0 ? n_out_max : 1;
   const int W = (int)dgr_kmap_mask_words(nmx);
   const int bpk = (W + kScanElems - 1) / kScanElems;
-  kmap_fill_kernel<<<dim3(bpk, K), kThreads, 0, (cudaStream_t)stream>>>(bits, W, block_cnt, out_coords, ncols, spec,
-                                                                        in_keys, in_vals, (uint64_t)in_cap - 1, offsets,
-                                                                        in_idx, out_idx);
+  kmap_fill_kernel<<<dim3(8 * bpk, K), kThreads, 0, (cudaStream_t)stream>>>(bits, W, bpk, block_cnt, out_coords, ncols,
+                                                                            spec, in_keys, in_vals, (uint64_t)in_cap - 1,
+                                                                            offsets, in_idx, out_idx);
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
@@ -606,15 +671,31 @@ int32_t dgr_kmap_fill(const uint32_t* bits, const int32_t* block_cnt, int32_t K,
 
 int32_t dgr_kmap_dense(const int32_t* out_coords, int64_t n_out_max, const int32_t* n_out_dev, int32_t ncols,
                        const dgr_keyspec_t* spec, const uint64_t* in_keys, const int32_t* in_vals, int64_t in_cap,
-                       const int32_t* offsets, int32_t K, int32_t* nbr, int64_t nbr_stride, void* stream) {
+                       const uint32_t* bloom_words, int64_t n_bloom_words, const int32_t* offsets, int32_t K,
+                       int32_t* nbr, int64_t nbr_stride, int32_t* hit_count, void* stream) {
   DGR_ARG_CHECK(in_cap > 0 && (in_cap & (in_cap - 1)) == 0, "capacity must be a power of two");
   DGR_ARG_CHECK(nbr_stride >= n_out_max, "row stride below the row bound");
+  if (hit_count != nullptr) DGR_CUDA_CHECK(cudaMemsetAsync(hit_count, 0, sizeof(int32_t), (cudaStream_t)stream));
+  DGR_ARG_CHECK(bloom_words == nullptr || (n_bloom_words >= 32 && (n_bloom_words & (n_bloom_words - 1)) == 0 &&
+                                           n_bloom_words <= 32768),
+                "bloom: power of two, 32..32768 words");
   if (n_out_max == 0) return DGR_OK;
-  const int k_per_block = 32;
-  const dim3 grid(dgr_blocks(n_out_max, kThreads), (K + k_per_block - 1) / k_per_block);
-  kmap_dense_kernel<<<grid, kThreads, k_per_block * 8, (cudaStream_t)stream>>>(
-      out_coords, n_out_dev, n_out_max, ncols, spec, in_keys, in_vals, (uint64_t)in_cap - 1, offsets, K, k_per_block,
-      nbr, nbr_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned row_blocks = dgr_blocks(n_out_max, kProbeThreads);
+  const int k_per_block = probe_k_per_block(K, row_blocks);
+  const dim3 grid(row_blocks, (K + k_per_block - 1) / k_per_block);
+  if (bloom_words != nullptr) {
+    const size_t smem = probe_smem_bytes(k_per_block, n_bloom_words);
+    DGR_ENSURE_SMEM((kmap_probe_kernel<true, true>), smem);
+    kmap_probe_kernel<true, true><<<grid, kProbeThreads, smem, st>>>(
+        out_coords, n_out_dev, n_out_max, ncols, spec, in_keys, in_vals, (uint64_t)in_cap - 1, bloom_words,
+        (uint32_t)n_bloom_words, offsets, K, k_per_block, nullptr, 0, nullptr, 0, nbr, nbr_stride, hit_count);
+  } else {
+    const size_t smem = probe_smem_bytes(k_per_block, 0);
+    kmap_probe_kernel<false, true><<<grid, kProbeThreads, smem, st>>>(
+        out_coords, n_out_dev, n_out_max, ncols, spec, in_keys, in_vals, (uint64_t)in_cap - 1, nullptr, 1u, offsets, K,
+        k_per_block, nullptr, 0, nullptr, 0, nbr, nbr_stride, hit_count);
+  }
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;

@@ -41,6 +41,11 @@ constexpr int kMetaNetBase = 8;       // meta[0..8): pair counts (N, N0, N1, key
 constexpr int kMetaPerMap = 5;
 constexpr int kKeyMargin = 32;        // spare cells around the bounding box (7^3 kernels, stride-8 flooring)
 
+int tc_variant();
+bool tc_f16_enabled();
+bool tc_os_enabled();
+int tc_pair_min_cout();
+
 #define DGR_TRY(expr)                 \
   do {                                \
     int32_t rc__ = (expr);            \
@@ -281,7 +286,7 @@ struct Level {
 
 struct KMap {
   int lin = 0, lout = 0, ksize = 3, K = 27;
-  bool dense = false;
+  bool dense = false;        // dense neighbour table instead of pair lists (conv1 table kernel, output-stationary layers)
   const int32_t* offsets = nullptr;
   uint32_t* bits = nullptr;
   int32_t* cnt = nullptr;
@@ -349,11 +354,11 @@ int32_t plan_begin(dgr_ctx* c, const dgr_net* net, Plan& p) {
   }
   // miss filters for the kernel maps with many offsets per row (6-D: 729)
   const bool use_bloom = p.D > 3;
-  if (use_bloom) {
+  if (use_bloom || net->conv1_ks > 3) {
     int64_t words = next_pow2((n_max * 10 + 31) / 32);
     if (words < 1024) words = 1024;
     if (words > 16384) words = 16384;
-    for (int l = 0; l < 4; ++l) {
+    for (int l = 0; l < (use_bloom ? 4 : 1); ++l) {       // 3-D: only the stride-1 table is probed with 5^3 / 7^3 offsets
       DGR_TRY(aalloc(c, words, &p.lv[l].bloom));
       p.lv[l].n_bloom = words;
       DGR_TRY(dgr_bloom2_build(p.lv[l].keys, p.lv[l].cap, p.lv[l].bloom, words, st));
@@ -369,7 +374,10 @@ int32_t plan_begin(dgr_ctx* c, const dgr_net* net, Plan& p) {
     for (int a = 0; a < p.D; ++a) m.K *= ksize;
     return p.n_maps++;
   };
-  for (int l = 0; l < 4; ++l) p.map_same[l] = add_map(l, l, 3, false);
+  // 3-D network: the stride-1 3^3 layers run output-stationary over a dense neighbour table (spconv_os.cu); the
+  // stride-1 map at level 0 keeps its pair lists when conv1 (one input channel, fp32 kernel) shares it
+  for (int l = 0; l < 4; ++l)
+    p.map_same[l] = add_map(l, l, 3, p.D == 3 && tc_os_enabled() && !(l == 0 && net->conv1_ks == 3));
   for (int l = 0; l < 3; ++l) p.map_down[l] = add_map(l, l + 1, 3, false);
   if (net->conv1_ks == 3) p.map_conv1 = p.map_same[0];
   else p.map_conv1 = add_map(0, 0, net->conv1_ks, conv1_uses_table(net));
@@ -382,9 +390,11 @@ int32_t plan_begin(dgr_ctx* c, const dgr_net* net, Plan& p) {
     if (m.dense) {
       m.nbr_stride = nmx;
       DGR_TRY(aalloc(c, (int64_t)m.K * nmx, &m.nbr));
-      DGR_TRY(dgr_kmap_dense(Lout.coords, Lout.n_max, Lout.n_dev, ncols, p.spec, Lin.keys, Lin.vals, Lin.cap, m.offsets,
-                             m.K, m.nbr, m.nbr_stride, st));
+      const bool bloom = Lin.bloom != nullptr && m.K > 27;
       DGR_CUDA_CHECK(cudaMemsetAsync(m.meta, 0, kMetaPerMap * sizeof(int32_t), (cudaStream_t)st));
+      DGR_TRY(dgr_kmap_dense(Lout.coords, Lout.n_max, Lout.n_dev, ncols, p.spec, Lin.keys, Lin.vals, Lin.cap,
+                             bloom ? Lin.bloom : nullptr, bloom ? Lin.n_bloom : 0, m.offsets, m.K, m.nbr, m.nbr_stride,
+                             m.meta, st));          // meta[0] = pairs P (for the roofline bookkeeping)
       continue;
     }
     DGR_TRY(aalloc(c, (int64_t)m.K * dgr_kmap_mask_words(nmx), &m.bits));
@@ -405,8 +415,12 @@ int32_t plan_finish(dgr_ctx* c, Plan& p) {
   for (int l = 1; l < 4; ++l) p.lv[l].n = mh[l];
   for (int i = 0; i < p.n_maps; ++i) {
     KMap& m = p.maps[i];
-    if (m.dense) continue;
     const int32_t* mm = mh + 4 + kMetaPerMap * i;
+    if (m.dense) {
+      m.P = mm[0];
+      m.nonempty = m.K;
+      continue;
+    }
     m.P = mm[0]; m.n_tiles = mm[1]; m.n_ptiles = mm[2]; m.nonempty = mm[3];
     if (mm[4] != 0) {
       dgr_set_error("coordinate extent does not fit a 63-bit packed key");
@@ -438,7 +452,8 @@ struct LayerExec {
   const KMap* map;
   bool transposed;
   int n_in, n_out;
-  bool table;
+  bool table;     // conv1: output-stationary fp32 table kernel (few input channels)
+  bool os;        // output-stationary tensor-core kernel with the fused epilogue
 };
 
 int tc_variant() {
@@ -456,6 +471,13 @@ bool tc_f16_enabled() {
   }();
   return v;
 }
+bool tc_os_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("DGR_TC_OS");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return v;
+}
 int tc_pair_min_cout() {
   static const int v = [] {
     const char* e = getenv("DGR_TC_PAIR_MIN_COUT");
@@ -464,7 +486,7 @@ int tc_pair_min_cout() {
   return v;
 }
 
-int32_t run_conv(dgr_ctx* c, const LayerExec& L, const float* feat, float* out) {
+int32_t run_conv(dgr_ctx* c, const LayerExec& L, const float* feat, const float* residual, int relu, float* out) {
   void* st = c->stream;
   const Conv& cv = *L.conv;
   const KMap& m = *L.map;
@@ -483,6 +505,10 @@ int32_t run_conv(dgr_ctx* c, const LayerExec& L, const float* feat, float* out) 
     DGR_TRY(dgr_spconv_table_fwd_strided(feat, cv.cin, cv.w, cv.cout, m.nbr, m.K, L.n_out, m.nbr_stride, cv.scale,
                                          cv.shift, out, st));
     rec.kind = 2;
+  } else if (L.os) {
+    DGR_TRY(dgr_spconv_os_fwd(feat, cv.cin, cv.packed, cv.cout, m.nbr, m.nbr_stride, m.K, L.n_out, cv.scale, cv.shift,
+                              residual, relu, out, st));
+    rec.kind = 3;
   } else {
     const int32_t* in_idx = L.transposed ? m.out_idx : m.in_idx;
     const int32_t* out_idx = L.transposed ? m.in_idx : m.out_idx;
@@ -527,32 +553,37 @@ int32_t run_network(dgr_ctx* c, const dgr_net* net, Plan& p, const float* feats_
   const int n[4] = {p.lv[0].n, p.lv[1].n, p.lv[2].n, p.lv[3].n};
   for (int s = 0; s < 4; ++s) {
     const KMap* m = s == 0 ? &p.maps[p.map_conv1] : &p.maps[p.map_down[s - 1]];
-    layers.push_back({&net->enc[s], m, false, s == 0 ? n[0] : n[s - 1], n[s], s == 0 && m->dense});
-    layers.push_back({&net->eb1[s], &p.maps[p.map_same[s]], false, n[s], n[s], false});
-    layers.push_back({&net->eb2[s], &p.maps[p.map_same[s]], false, n[s], n[s], false});
+    const bool os = p.maps[p.map_same[s]].dense;
+    layers.push_back({&net->enc[s], m, false, s == 0 ? n[0] : n[s - 1], n[s], s == 0 && m->dense && m != &p.maps[p.map_same[0]], false});
+    layers.push_back({&net->eb1[s], &p.maps[p.map_same[s]], false, n[s], n[s], false, os});
+    layers.push_back({&net->eb2[s], &p.maps[p.map_same[s]], false, n[s], n[s], false, os});
   }
   for (int d = 0; d < 3; ++d) {
     const int lo = 2 - d;       // output level index
-    layers.push_back({&net->dec[d], &p.maps[p.map_down[lo]], true, n[lo + 1], n[lo], false});
-    layers.push_back({&net->db1[d], &p.maps[p.map_same[lo]], false, n[lo], n[lo], false});
-    layers.push_back({&net->db2[d], &p.maps[p.map_same[lo]], false, n[lo], n[lo], false});
+    const bool os = p.maps[p.map_same[lo]].dense;
+    layers.push_back({&net->dec[d], &p.maps[p.map_down[lo]], true, n[lo + 1], n[lo], false, false});
+    layers.push_back({&net->db1[d], &p.maps[p.map_same[lo]], false, n[lo], n[lo], false, os});
+    layers.push_back({&net->db2[d], &p.maps[p.map_same[lo]], false, n[lo], n[lo], false, os});
   }
   // one slab for every convolution output, zero-filled once (the scatter-add kernels accumulate)
-  int64_t total = 0;
-  for (auto& L : layers) total += (int64_t)L.n_out * L.conv->cout;
-  float* slab;
+  // (output-stationary layers write every row themselves: their outputs live outside the zeroed slab)
+  int64_t total = 0, total_os = 0;
+  for (auto& L : layers) (L.table || L.os ? total_os : total) += (int64_t)L.n_out * L.conv->cout;
+  float *slab, *slab_os;
   DGR_TRY(aalloc(c, total, &slab));
-  DGR_CUDA_CHECK(cudaMemsetAsync(slab, 0, (size_t)total * sizeof(float), c->stream));
-  int64_t ofs = 0;
+  DGR_TRY(aalloc(c, total_os, &slab_os));
+  if (total > 0) DGR_CUDA_CHECK(cudaMemsetAsync(slab, 0, (size_t)total * sizeof(float), c->stream));
+  int64_t ofs = 0, ofs_os = 0;
   auto take = [&](const LayerExec& L) {
-    float* b = slab + ofs;
-    ofs += (int64_t)L.n_out * L.conv->cout;
+    const bool direct = L.table || L.os;
+    float* b = direct ? slab_os + ofs_os : slab + ofs;
+    (direct ? ofs_os : ofs) += (int64_t)L.n_out * L.conv->cout;
     return b;
   };
   auto conv_bn = [&](const LayerExec& L, const float* feat, const float* residual, int relu, float** res) -> int32_t {
     float* o = take(L);
-    DGR_TRY(run_conv(c, L, feat, o));
-    if (!L.table)
+    DGR_TRY(run_conv(c, L, feat, residual, relu, o));
+    if (!L.table && !L.os)
       DGR_TRY(dgr_affine_act(o, L.n_out, L.conv->cout, L.conv->scale, L.conv->shift, residual, relu, o, st));
     *res = o;
     return DGR_OK;

@@ -371,6 +371,57 @@ __global__ void l2_normalize_kernel(const float* __restrict__ x, int64_t n, int 
   for (int ch = lane; ch < c; ch += 32) out[row * c + ch] = x[row * c + ch] * inv;
 }
 
+// ---------------------------------------------------------------------------------------
+// weight gradient (training): dW[kappa] = sum_{p in bucket kappa} in[i_p]^T (x) gout[j_p]
+// One block per (kappa, 32 input channels, 64 output channels); pairs are staged 32 at a time in shared
+// memory (row gathers, coalesced along the channels); every block sums its bucket in order: deterministic.
+// ---------------------------------------------------------------------------------------
+constexpr int kWgCi = 32, kWgCo = 64, kWgP = 32;
+__global__ void __launch_bounds__(kThreads)
+spconv_wgrad_kernel(const float* __restrict__ in_feat, int cin, const float* __restrict__ gout, int cout,
+                    const int32_t* __restrict__ in_idx, const int32_t* __restrict__ out_idx,
+                    const int32_t* __restrict__ kofs, float* __restrict__ dw) {
+  __shared__ float As[kWgP][kWgCi + 1];
+  __shared__ float Bs[kWgP][kWgCo];
+  const int kappa = blockIdx.x;
+  const int ci0 = blockIdx.y * kWgCi, co0 = blockIdx.z * kWgCo;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;      // 16 x 16 threads: 2 ci rows x 4 co columns each
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const int p_begin = kofs[kappa], p_end = kofs[kappa + 1];
+  for (int p0 = p_begin; p0 < p_end; p0 += kWgP) {
+    const int np = min(kWgP, p_end - p0);
+    for (int e = t; e < kWgP * kWgCi; e += kThreads) {
+      const int pp = e / kWgCi, c = e % kWgCi;
+      As[pp][c] = (pp < np && ci0 + c < cin) ? in_feat[(size_t)in_idx[p0 + pp] * cin + ci0 + c] : 0.f;
+    }
+    for (int e = t; e < kWgP * kWgCo; e += kThreads) {
+      const int pp = e / kWgCo, c = e % kWgCo;
+      Bs[pp][c] = (pp < np && co0 + c < cout) ? gout[(size_t)out_idx[p0 + pp] * cout + co0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pp = 0; pp < kWgP; ++pp) {
+      const float a0 = As[pp][2 * ty], a1 = As[pp][2 * ty + 1];
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[pp][4 * tx]);
+      acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int ci = ci0 + 2 * ty + r;
+    if (ci >= cin) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int co = co0 + 4 * tx + c;
+      if (co < cout) dw[((size_t)kappa * cin + ci) * cout + co] = acc[r][c];
+    }
+  }
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -478,6 +529,23 @@ int32_t dgr_cat2(const float* a, int32_t ca, const float* b, int32_t cb, int64_t
   if (n == 0) return DGR_OK;
   cat2_kernel<<<dgr_blocks(n * (ca + cb), kThreads), kThreads, 0, (cudaStream_t)stream>>>(a, ca, b, cb, n,
                                                                                        out);
+  dgr_note_launches(1);
+  DGR_LAUNCH_CHECK();
+  return DGR_OK;
+}
+
+// Weight gradient of dgr_spconv_fwd / dgr_spconv_tc_fwd (training): dw[K, cin, cout] is overwritten with
+// dw[kappa] = sum over the pairs p of bucket kappa of in_feat[in_idx[p], :]^T (x) grad_out[out_idx[p], :].
+// The input gradient needs no kernel of its own: it is dgr_spconv_fwd on grad_out with the index lists
+// exchanged and every W[kappa] transposed.
+int32_t dgr_spconv_wgrad(const float* in_feat, int32_t cin, const float* grad_out, int32_t cout,
+                         const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs, int32_t K, float* dw,
+                         void* stream) {
+  DGR_ARG_CHECK(K >= 1 && cin >= 1 && cout >= 1, "bad shape");
+  DGR_ARG_CHECK((cin + kWgCi - 1) / kWgCi <= 65535 && (cout + kWgCo - 1) / kWgCo <= 65535, "too many channels");
+  const dim3 grid(K, (cin + kWgCi - 1) / kWgCi, (cout + kWgCo - 1) / kWgCo);
+  spconv_wgrad_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(in_feat, cin, grad_out, cout, in_idx, out_idx, kofs,
+                                                                    dw);
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;

@@ -232,7 +232,7 @@ def main(argv=None):
     print(json.dumps(dict(summary, world_size=world)))          # the summary first: a failing save loses nothing
     out = os.path.join(out_dir, 'dgr-b200-stats.npz')
     np.savez(out, stats=result['stats'][None], names=['DGR'], poses=result['poses'], groups=result['groups'])
-    print(json.dumps(dict(saved=out)))
+    print(json.dumps(dict(summary, world_size=world, saved=out)))
   if world > 1:
     dist.destroy_process_group()
 

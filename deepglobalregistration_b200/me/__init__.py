@@ -48,6 +48,47 @@ def sparse_conv(feat, conv_mod, km, out):
   return _abi.spconv_fwd(feat, conv_mod.kernel.detach(), km, out)
 
 
+def needs_grad(*tensors):
+  """Training path: autograd is on and one of the tensors is part of a graph."""
+  return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class SparseConvFunction(torch.autograd.Function):
+  """Sparse convolution with a backward pass, for training (core/trainer.py:204-264 calls loss.backward()
+  through MinkowskiConvolution / MinkowskiConvolutionTranspose).  Forward: the gather-GEMM-scatter kernels;
+  backward: the input gradient is the same kernel on grad_out over the map with its index lists exchanged and
+  every W[kappa] transposed, the weight gradient is dgr_spconv_wgrad (per-offset A^T B, deterministic)."""
+
+  @staticmethod
+  def forward(ctx, feat, weight, km, n_out):
+    feat, weight = feat.contiguous(), weight.contiguous()
+    cin, cout = feat.shape[1], weight.shape[-1]
+    out = torch.zeros(n_out, cout, dtype=torch.float32, device=feat.device)
+    if _CONV_MODE != 'simt' and _abi.tc_supported(cin, cout):
+      _abi.spconv_tc_fwd(feat, _abi.pack_weight_tf32(weight.detach(), km.K, cin, cout), km, out,
+                         passes=3 if _CONV_MODE == 'tc3' else 1)
+    else:
+      _abi.spconv_fwd(feat, weight.detach().reshape(km.K, cin, cout), km, out)
+    ctx.save_for_backward(feat, weight)
+    ctx.km = km
+    return out
+
+  @staticmethod
+  def backward(ctx, grad_out):
+    feat, weight = ctx.saved_tensors
+    km = ctx.km
+    grad_out = grad_out.contiguous()
+    cin, cout = feat.shape[1], grad_out.shape[1]
+    w3 = weight.detach().reshape(km.K, cin, cout)
+    grad_feat = grad_w = None
+    if ctx.needs_input_grad[0]:
+      grad_feat = torch.zeros_like(feat)
+      _abi.spconv_fwd(grad_out, w3.transpose(1, 2).contiguous(), km.transposed(), grad_feat)
+    if ctx.needs_input_grad[1]:
+      grad_w = _abi.spconv_wgrad(feat, grad_out, km).reshape(weight.shape)
+    return grad_feat, grad_w, None, None
+
+
 class RegionType(Enum):
   HYPER_CUBE = 0
   HYPER_CROSS = 1
@@ -189,11 +230,16 @@ class SparseTensor:
 
   def __iadd__(self, other):           # out += residual  (model/residual_block.py:131)
     self._check_same_map(other)
-    self._F = _abi.affine_act(self._F, residual=other._F, out=self._F)
+    if needs_grad(self._F, other._F):
+      self._F = self._F + other._F
+    else:
+      self._F = _abi.affine_act(self._F, residual=other._F, out=self._F)
     return self
 
   def __add__(self, other):
     self._check_same_map(other)
+    if needs_grad(self._F, other._F):
+      return self._like(self._F + other._F)
     return self._like(_abi.affine_act(self._F, residual=other._F))
 
   def __repr__(self):
@@ -207,7 +253,7 @@ def cat(*tensors):
   out = tensors[0]
   for t in tensors[1:]:
     out._check_same_map(t)
-    out = out._like(_abi.cat2(out.F, t.F))
+    out = out._like(torch.cat((out.F, t.F), 1) if needs_grad(out.F, t.F) else _abi.cat2(out.F, t.F))
   return out
 
 
@@ -266,17 +312,25 @@ class _ConvBase(nn.Module):
   def forward(self, x):
     assert isinstance(x, SparseTensor), 'input must be a SparseTensor'
     assert x.D == self.dimension
-    if torch.is_grad_enabled() and (self.kernel.requires_grad and self.training):
-      raise NotImplementedError('dgr_b200 implements the forward pass only (training is outside the '
-                                'built hot path)')
     man, key = x.coordinate_manager, x.coordinate_map_key
+    # training path: a graph reaches this layer through its input, or the module is in train() mode with
+    # trainable parameters; eval-mode inference stays on the forward-only kernels even outside no_grad()
+    train = needs_grad(x.F) or (self.training and needs_grad(self.kernel, self.bias))
     if self.use_mm:
+      if train:           # 1x1 convolution = a dense layer: torch supplies forward and backward
+        out = x.F @ self.kernel
+        return x._like(out if self.bias is None else out + self.bias)
       return x._like(_abi.linear_fwd(x.F, self.kernel.detach(), None if self.bias is None
                                      else self.bias.detach()))
     if self.IS_TRANSPOSE:
       out_key, km = man.transpose_kernel_map(key, self.stride, self.kernel_size)
     else:
       out_key, km = man.kernel_map(key, self.stride, self.kernel_size)
+    if train:
+      out = SparseConvFunction.apply(x.F, self.kernel, km, km.n_out)
+      if self.bias is not None:
+        out = out + self.bias
+      return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=man)
     w = self.kernel.detach()
     if (not self.IS_TRANSPOSE) and km.nbr is not None and self.in_channels <= 8 and \
         self.out_channels in (16, 32, 64):
@@ -326,14 +380,18 @@ class MinkowskiBatchNorm(nn.Module):
     return self._folded[1], self._folded[2]
 
   def forward(self, x):
-    if self.training:
-      raise NotImplementedError('dgr_b200 implements evaluation-mode BatchNorm only; call .eval()')
+    if self.training or needs_grad(x.F):
+      # training: batch statistics + running-stat update are nn.BatchNorm1d's, exactly what ME's
+      # MinkowskiBatchNorm does (it applies its wrapped BatchNorm1d to the feature matrix)
+      return x._like(self.bn(x.F))
     scale, shift = self.folded()
     return x._like(_abi.affine_act(x.F, scale=scale, shift=shift))
 
 
 class MinkowskiReLU(nn.Module):
   def forward(self, x):
+    if needs_grad(x.F):
+      return x._like(torch.relu(x.F))
     return x._like(_abi.affine_act(x.F, relu=True))
 
 

@@ -276,6 +276,15 @@ int32_t dgr_spconv_table_fwd_strided(const float* in_feat, int32_t cin, const fl
                                      const int32_t* nbr, int32_t K, int64_t n_out, int64_t nbr_stride,
                                      const float* scale, const float* shift, float* out, void* stream);
 
+/* ---- training: backward of the sparse convolution
+ *      (core/trainer.py:204-264 -> loss.backward() through MinkowskiConvolution) -------------- */
+/* dw[K, cin, cout] (overwritten) = weight gradient: dw[kappa] = sum over pairs p of bucket kappa of
+ * in_feat[in_idx[p], :]^T (x) grad_out[out_idx[p], :]; deterministic (in-order sums per block).
+ * The input gradient is dgr_spconv_fwd(grad_out, W^T) with in_idx / out_idx exchanged. */
+int32_t dgr_spconv_wgrad(const float* in_feat, int32_t cin, const float* grad_out, int32_t cout,
+                         const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs, int32_t K, float* dw,
+                         void* stream);
+
 /* ---- 3xFP16 mode of the cta_group::2 tensor-core convolution ---------------------------------
  * fp16 has TF32's 11 significant bits at half the bytes and twice the tensor rate; operands are scaled by
  * powers of two (exact) so that the tensor's absolute maximum lands in [2^14, 2^15), then split hi / lo as
@@ -336,10 +345,25 @@ int32_t dgr_kmap_fill(const uint32_t* bits, const int32_t* block_cnt, int32_t K,
                       const int32_t* out_coords, int32_t ncols, const dgr_keyspec_t* spec, const uint64_t* in_keys,
                       const int32_t* in_vals, int64_t in_cap, const int32_t* offsets, int32_t* in_idx,
                       int32_t* out_idx, void* stream);
-/* Dense neighbour table nbr[kappa * nbr_stride + j] (-1 = no neighbour) with a device-side row count. */
+/* Dense neighbour table nbr[kappa * nbr_stride + j] (-1 = no neighbour) with a device-side row count;
+ * bloom_words optional as in dgr_kmap_probe; hit_count (optional device int32, zeroed by the call) receives
+ * the number of pairs P. */
 int32_t dgr_kmap_dense(const int32_t* out_coords, int64_t n_out_max, const int32_t* n_out_dev, int32_t ncols,
                        const dgr_keyspec_t* spec, const uint64_t* in_keys, const int32_t* in_vals, int64_t in_cap,
-                       const int32_t* offsets, int32_t K, int32_t* nbr, int64_t nbr_stride, void* stream);
+                       const uint32_t* bloom_words, int64_t n_bloom_words, const int32_t* offsets, int32_t K,
+                       int32_t* nbr, int64_t nbr_stride, int32_t* hit_count, void* stream);
+
+/* ---- output-stationary tensor-core convolution with the fused layer epilogue (csrc/spconv_os.cu) ----------
+ * For stride-1 layers whose neighbour table is dense enough (3^3 kernels of the 3-D network, ~64 % occupied):
+ *   out[j, :] = act((sum_kappa in_feat[nbr[kappa * nbr_stride + j], :] @ W[kappa]) * scale + shift + residual[j, :])
+ * tile = 128 output rows, accumulator in TMEM across all offsets, 3xTF32 from the packed slabs of
+ * dgr_pack_weight_tf32; every output row is written once with plain stores (no atomics, no pre-zeroed buffer,
+ * deterministic); eval BatchNorm (model/common.py:13), the residual add and ReLU of BasicBlockBase.forward
+ * (model/residual_block.py:118-134) ride in the epilogue.  scale / shift / residual may be NULL. */
+int32_t dgr_spconv_os_supported(int32_t cin, int32_t cout);          /* both % 32 == 0, cout <= 256 */
+int32_t dgr_spconv_os_fwd(const float* in_feat, int32_t cin, const float* weight_t, int32_t cout, const int32_t* nbr,
+                          int64_t nbr_stride, int32_t K, int64_t n_out, const float* scale, const float* shift,
+                          const float* residual, int32_t relu, float* out, void* stream);
 
 /* ---- native executor (csrc/exec.cu) ------------------------------------------------------
  * A context owns a stream (or uses the one given), a grow-only device arena and pinned staging; calls

@@ -152,9 +152,20 @@ def test_strided_kernel_map_and_dense_table(abi):
   stride = n + 100
   nbr = torch.full((343, stride), -5, dtype=torch.int32, device='cuda')
   n_dev = torch.tensor([n], dtype=torch.int32, device='cuda')
-  abi.call('dgr_kmap_dense', abi.ptr(_padded(coords, 100)), n + 100, abi.ptr(n_dev), 4, abi.ptr(spec), abi.ptr(table.keys),
-           abi.ptr(table.vals), table.cap, abi.ptr(offs7), 343, abi.ptr(nbr), stride, abi.stream())
+  padded = _padded(coords, 100)
+  abi.call('dgr_kmap_dense', abi.ptr(padded), n + 100, abi.ptr(n_dev), 4, abi.ptr(spec), abi.ptr(table.keys),
+           abi.ptr(table.vals), table.cap, None, 0, abi.ptr(offs7), 343, abi.ptr(nbr), stride, None, abi.stream())
   assert torch.equal(nbr[:, :n], km7.nbr) and bool((nbr[:, n:] == -5).all())
+  # with the shared-memory miss filter
+  words = torch.empty(2048, dtype=torch.int32, device='cuda')
+  abi.call('dgr_bloom2_build', abi.ptr(table.keys), table.cap, abi.ptr(words), 2048, abi.stream())
+  nbr2 = torch.full((343, stride), -5, dtype=torch.int32, device='cuda')
+  hits = torch.full((1,), 77, dtype=torch.int32, device='cuda')
+  abi.call('dgr_kmap_dense', abi.ptr(padded), n + 100, abi.ptr(n_dev), 4, abi.ptr(spec), abi.ptr(table.keys),
+           abi.ptr(table.vals), table.cap, abi.ptr(words), 2048, abi.ptr(offs7), 343, abi.ptr(nbr2), stride, abi.ptr(hits),
+           abi.stream())
+  assert torch.equal(nbr2[:, :n], km7.nbr) and bool((nbr2[:, n:] == -5).all())
+  assert int(hits) == km7.n_pairs
 
 
 @pytest.fixture(scope='module')
@@ -310,3 +321,48 @@ def test_conv_3xfp16_matches_fp32_and_3xtf32(abi, D, cin, cout, n, ext, scale):
   e32 = float((out32.double() - ref64).abs().max()) / mag
   print(f'D={D} {cin}->{cout} scale {scale}: 3xFP16 err {e16:.2e}, 3xTF32 err {e32:.2e} (relative to max |out|)')
   assert e16 <= 2e-6 and e16 <= 4 * e32 + 2e-7, (e16, e32)
+
+
+@pytest.mark.parametrize('cin,cout,n,ext', [(32, 32, 6000, 11), (64, 64, 3000, 9), (128, 128, 900, 6), (256, 256, 700, 6),
+                                             (64, 32, 150, 3), (32, 96, 5000, 10)])
+def test_output_stationary_conv_with_fused_epilogue(abi, cin, cout, n, ext):
+  """dgr_spconv_os_fwd (tile = 128 output rows, accumulator across all 27 offsets, BatchNorm / residual / ReLU in
+  the epilogue) against the weight-stationary kernel + dgr_affine_act, and against a float64 reference."""
+  from deepglobalregistration_b200.me.coords import CoordinateMapKey, kernel_offsets
+  coords = _cloud(3, n, ext, seed=cin + cout + n)
+  ct = torch.from_numpy(coords).cuda().contiguous()
+  man, spec, table = _spec_and_table(abi, ct)
+  _, km = man.kernel_map(CoordinateMapKey(1), 1, 3)
+  nrow = len(coords)
+  nbr = torch.empty(27, nrow, dtype=torch.int32, device='cuda')
+  offs = kernel_offsets(3, 3, 1, torch.device('cuda'))
+  abi.call('dgr_kmap_dense', abi.ptr(ct), nrow, None, 4, abi.ptr(spec), abi.ptr(table.keys), abi.ptr(table.vals),
+           table.cap, None, 0, abi.ptr(offs), 27, abi.ptr(nbr), nrow, None, abi.stream())
+  g = torch.Generator().manual_seed(n)
+  feat = torch.randn(nrow, cin, generator=g).cuda()
+  W = (torch.randn(27, cin, cout, generator=g) / np.sqrt(cin * 17)).cuda().contiguous()
+  scale = (1 + 0.1 * torch.randn(cout, generator=g)).cuda()
+  shift = (0.1 * torch.randn(cout, generator=g)).cuda()
+  res = torch.randn(nrow, cout, generator=g).cuda()
+  Wt = abi.pack_weight_tf32(W, 27, cin, cout)
+  # float64 reference through the pair lists
+  ref = torch.zeros(nrow, cout, dtype=torch.float64, device='cuda')
+  ii, jj, kofs = km.in_idx[:km.n_pairs].long(), km.out_idx[:km.n_pairs].long(), km.kofs_host
+  for kap in range(27):
+    a, b = int(kofs[kap]), int(kofs[kap + 1])
+    if b > a:
+      ref.index_add_(0, jj[a:b], feat[ii[a:b]].double() @ W[kap].double())
+  for use_affine, use_res, relu in ((True, True, True), (True, False, True), (False, False, False)):
+    want = ref * scale.double() + shift.double() if use_affine else ref.clone()
+    if use_res:
+      want = want + res.double()
+    if relu:
+      want = want.clamp_min(0)
+    got = abi.spconv_os_fwd(feat, Wt, nbr, cout, scale if use_affine else None, shift if use_affine else None,
+                            res if use_res else None, relu)
+    torch.cuda.synchronize()
+    err = float((got.double() - want).abs().max()) / (1 + float(want.abs().max()))
+    assert err <= 2e-6, (use_affine, use_res, relu, err)
+    got2 = abi.spconv_os_fwd(feat, Wt, nbr, cout, scale if use_affine else None, shift if use_affine else None,
+                             res if use_res else None, relu)
+    assert torch.equal(got, got2)          # deterministic: no atomics
