@@ -78,9 +78,11 @@ SIGNATURES = {
     'dgr_kmap_probe': [_p, _i64, _p, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p],
     'dgr_kmap_fill': [_p, _p, _i32, _i64, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p],
     'dgr_kmap_dense': [_p, _i64, _p, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i32, _p, _i64, _p, _p],
+    'dgr_spconv_ones_bits_fwd': [_p, _i32, _p, _i64, _i32, _i64, _p, _p, _p, _p],
     'dgr_spconv_os_supported': [_i32, _i32],
     'dgr_spconv_os_fwd': [_p, _i32, _p, _i32, _p, _i64, _i32, _i64, _p, _p, _p, _i32, _p, _p],
     'dgr_spconv_wgrad': [_p, _i32, _p, _i32, _p, _p, _p, _i32, _p, _p],
+    'dgr_affine_act_amax': [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p],
     'dgr_absmax_f32': [_p, _i64, _p, _p],
     'dgr_spconv_tc_f16_supported': [_i32, _i32],
     'dgr_pack_weight_f16': [_p, _i32, _i32, _i32, _p, _p, _p],

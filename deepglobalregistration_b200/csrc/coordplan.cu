@@ -28,7 +28,8 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kScanElems = 2048;      // elements per block in flag / mask scans (256 threads x 8)
+constexpr int kScanElems = 2048;      // elements per block in the flag scans of the coarse maps (256 threads x 8)
+constexpr int kCntWords = 256;        // mask words per counted block of a kernel map (one fill block, one word per thread)
 constexpr int kProbeThreads = 512;    // 16 warps = 512 output rows per probe block
 constexpr int kMaxLevels = 4;
 
@@ -276,7 +277,7 @@ __global__ void bloom2_build_kernel(const uint64_t* __restrict__ keys, int64_t c
 // Probing in place instead would make the whole warp wait for an L2 round trip whenever ANY of its 32 lanes
 // passes the filter (a 3 % pass rate per lane is 62 % per warp) with one or two lanes doing useful work.
 // Output: kDense ? nbr[kappa * nbr_stride + j] = input row or -1
-//                : bits[kappa * W + w] = ballot of warp w's rows (+ per-(kappa, 2048-word block) counts)
+//                : bits[kappa * W + w] = ballot of warp w's rows (+ per-(kappa, 256-word block) counts)
 template <bool kBloom, bool kDense>
 __global__ void __launch_bounds__(kProbeThreads, 2)
 kmap_probe_kernel(const int32_t* __restrict__ out_coords, const int32_t* __restrict__ n_out_dev, int64_t n_out_max,
@@ -357,7 +358,7 @@ kmap_probe_kernel(const int32_t* __restrict__ out_coords, const int32_t* __restr
   if (!kBloom && !kDense) {
     // no filter (3^3 kernels: ~60 % of the probes hit): probe in place, four independent lookups in flight
     const int w = (int)(j >> 5);
-    const int cnt_col = w / kScanElems;
+    const int cnt_col = w / kCntWords;
     for (int kk = 0; kk < kn; kk += 4) {
       bool found[4];
 #pragma unroll
@@ -395,7 +396,7 @@ kmap_probe_kernel(const int32_t* __restrict__ out_coords, const int32_t* __restr
     __syncwarp();
     const int w = (int)(j >> 5);
     if (w < W) {
-      const int cnt_col = w / kScanElems;
+      const int cnt_col = w / kCntWords;
       for (int kk = lane; kk < kn; kk += 32) {
         const uint32_t m = mt[kk];
         bits[(int64_t)(k0 + kk) * W + w] = m;
@@ -448,11 +449,11 @@ __global__ void kmap_scan_kernel(int32_t* cnt, int K, int bpk, int tile_rows, in
   }
 }
 
-// Fill: grid (8 * bpk, K); block (x, kappa) owns the 256 mask words [x * 256, +256) of bucket kappa, one per
-// thread.  A word's 32 hits are resolved by the 32 LANES of a warp in parallel (each lane: one hash lookup,
-// consecutive output positions), so the longest serial chain is the 32 words of a warp, not the hits of a
-// thread.  Offsets: the scanned count of the enclosing 2048-word block, plus the set bits of the 256-word
-// sub-blocks before this one, plus the in-block exclusive scan.
+// Fill: grid (bpk, K); block (b, kappa) owns the 256 mask words [b * 256, +256) of bucket kappa, one per thread;
+// its output offset is the scanned count of exactly that block, so blocks without a hit leave at once (a 6-D
+// map at stride 1 has a hit in ~10 % of its blocks).  A word's 32 hits are resolved by the 32 LANES of a warp in
+// parallel (each lane: one hash lookup, consecutive output positions): the longest serial chain is the 32 words
+// of a warp, not the hits of a thread.
 __global__ void __launch_bounds__(kThreads)
 kmap_fill_kernel(const uint32_t* __restrict__ bits, int W, int bpk, const int32_t* __restrict__ block_ofs,
                  const int32_t* __restrict__ out_coords, int ncols, const dgr_keyspec_t* __restrict__ spec_p,
@@ -460,39 +461,22 @@ kmap_fill_kernel(const uint32_t* __restrict__ bits, int W, int bpk, const int32_
                  const int32_t* __restrict__ offsets, int32_t* __restrict__ in_idx, int32_t* __restrict__ out_idx) {
   __shared__ uint32_t s_mask[kThreads];
   __shared__ int s_base[kThreads];
-  __shared__ int s_red[kThreads / 32];
   const int kappa = blockIdx.y;
-  const int sub = blockIdx.x & 7, grp = blockIdx.x >> 3;       // 8 sub-blocks of 256 words per 2048-word block
+  const int64_t e = (int64_t)kappa * bpk + blockIdx.x;
+  const int base = block_ofs[e];
+  if (block_ofs[e + 1] == base) return;                        // no pair in this block (uniform)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int64_t row_base = (int64_t)kappa * W;
-  const int w_grp = grp * kScanElems;
-  // set bits of this group's sub-blocks before `sub`
-  int before = 0;
-  for (int q = 0; q < sub; ++q) {
-    const int w = w_grp + q * kThreads + t;
-    if (w < W) before += __popc(bits[row_base + w]);
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
-  if (lane == 0) s_red[warp] = before;
-  const int w_own = w_grp + sub * kThreads + t;
-  const uint32_t m_own = w_own < W ? bits[row_base + w_own] : 0u;
-  __syncthreads();
-  int prior = 0;
-#pragma unroll
-  for (int k = 0; k < kThreads / 32; ++k) prior += s_red[k];
-  __syncthreads();
-  int total = 0;
-  const int excl = dgr_block_exclusive_scan_256(__popc(m_own), &total);
-  if (total == 0) return;                                      // uniform
+  const int w_own = blockIdx.x * kCntWords + t;
+  const uint32_t m_own = w_own < W ? bits[(int64_t)kappa * W + w_own] : 0u;
+  const int excl = dgr_block_exclusive_scan_256(__popc(m_own), nullptr);
   s_mask[t] = m_own;
-  s_base[t] = block_ofs[(int64_t)kappa * bpk + grp] + prior + excl;
+  s_base[t] = base + excl;
   __syncthreads();
   const dgr_keyspec_t s = *spec_p;
   long long d = 0;
   const int32_t* o = offsets + (int64_t)kappa * (ncols - 1);
   for (int a = 0; a < ncols - 1; ++a) d += (long long)o[a] * (1ll << s.shift[a + 1]);
-  const int w_first = w_grp + sub * kThreads + warp * 32;      // this warp resolves its own 32 words
+  const int w_first = blockIdx.x * kCntWords + warp * 32;      // this warp resolves its own 32 words
   for (int u = 0; u < 32; ++u) {
     const uint32_t m = s_mask[warp * 32 + u];
     if (m == 0u) continue;                                     // uniform
@@ -604,7 +588,7 @@ int64_t dgr_kmap_mask_words(int64_t n_out_max) {
 /* ints of the block-count workspace: K * ceil(W / 2048) + 2 */
 int64_t dgr_kmap_cnt_elems(int32_t K, int64_t n_out_max) {
   const int64_t W = dgr_kmap_mask_words(n_out_max);
-  return (int64_t)K * ((W + kScanElems - 1) / kScanElems) + 2;
+  return (int64_t)K * ((W + kCntWords - 1) / kCntWords) + 2;
 }
 
 static size_t probe_smem_bytes(int k_per_block, int64_t n_bloom_words) {
@@ -631,7 +615,7 @@ int32_t dgr_kmap_probe(const int32_t* out_coords, int64_t n_out_max, const int32
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nmx = n_out_max > 0 ? n_out_max : 1;
   const int W = (int)dgr_kmap_mask_words(nmx);
-  const int bpk = (W + kScanElems - 1) / kScanElems;
+  const int bpk = (W + kCntWords - 1) / kCntWords;
   DGR_CUDA_CHECK(cudaMemsetAsync(block_cnt, 0, (size_t)dgr_kmap_cnt_elems(K, nmx) * sizeof(int32_t), st));
   const unsigned row_blocks = dgr_blocks(nmx, kProbeThreads);
   const int k_per_block = probe_k_per_block(K, row_blocks);
@@ -660,8 +644,8 @@ int32_t dgr_kmap_fill(const uint32_t* bits, const int32_t* block_cnt, int32_t K,
                       int32_t* in_idx, int32_t* out_idx, void* stream) {
   const int64_t nmx = n_out_max > 0 ? n_out_max : 1;
   const int W = (int)dgr_kmap_mask_words(nmx);
-  const int bpk = (W + kScanElems - 1) / kScanElems;
-  kmap_fill_kernel<<<dim3(8 * bpk, K), kThreads, 0, (cudaStream_t)stream>>>(bits, W, bpk, block_cnt, out_coords, ncols,
+  const int bpk = (W + kCntWords - 1) / kCntWords;
+  kmap_fill_kernel<<<dim3(bpk, K), kThreads, 0, (cudaStream_t)stream>>>(bits, W, bpk, block_cnt, out_coords, ncols,
                                                                             spec, in_keys, in_vals, (uint64_t)in_cap - 1,
                                                                             offsets, in_idx, out_idx);
   dgr_note_launches(1);

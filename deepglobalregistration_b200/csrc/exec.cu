@@ -163,6 +163,7 @@ struct dgr_ctx {
   std::vector<ProfileRec> prof;
   std::vector<cudaEvent_t> event_pool;
   std::vector<cudaEvent_t> stage_marks;        // stage boundaries of the last pair (profiling on)
+  std::map<const float*, float*> amax_of;      // activation tensor -> device slot holding max |x| (current network)
   // taps of the last pair (device pointers into the arena, valid until the next call on this context)
   struct Tap {
     const void* p = nullptr;
@@ -206,6 +207,7 @@ struct dgr_net {
   const float* final_b = nullptr;
   std::vector<float*> owned;
   int device = 0;
+  bool os_level[4] = {false, false, false, false};   // stride-1 3^3 layers of level l run output-stationary
 };
 
 namespace {
@@ -287,6 +289,8 @@ struct Level {
 struct KMap {
   int lin = 0, lout = 0, ksize = 3, K = 27;
   bool dense = false;        // dense neighbour table instead of pair lists (conv1 table kernel, output-stationary layers)
+  bool bits_only = false;    // occupancy masks only: conv1 of a network whose single input channel is all ones
+  int64_t W = 0;             // mask words per offset
   const int32_t* offsets = nullptr;
   uint32_t* bits = nullptr;
   int32_t* cnt = nullptr;
@@ -307,6 +311,7 @@ struct Plan {
   int n_maps = 0;
   int map_conv1 = 0, map_same[4] = {0, 0, 0, 0}, map_down[3] = {0, 0, 0};
   int meta_base = kMetaNetBase;
+  bool input_ones = false;   // the network input is one channel of ones (FCGF / inlier 'ones'): conv1 needs occupancy only
 };
 
 bool conv1_uses_table(const dgr_net* net) {
@@ -377,10 +382,15 @@ int32_t plan_begin(dgr_ctx* c, const dgr_net* net, Plan& p) {
   // 3-D network: the stride-1 3^3 layers run output-stationary over a dense neighbour table (spconv_os.cu); the
   // stride-1 map at level 0 keeps its pair lists when conv1 (one input channel, fp32 kernel) shares it
   for (int l = 0; l < 4; ++l)
-    p.map_same[l] = add_map(l, l, 3, p.D == 3 && tc_os_enabled() && !(l == 0 && net->conv1_ks == 3));
+    p.map_same[l] = add_map(l, l, 3, net->os_level[l]);
   for (int l = 0; l < 3; ++l) p.map_down[l] = add_map(l, l + 1, 3, false);
-  if (net->conv1_ks == 3) p.map_conv1 = p.map_same[0];
-  else p.map_conv1 = add_map(0, 0, net->conv1_ks, conv1_uses_table(net));
+  if (net->conv1_ks == 3) {
+    p.map_conv1 = p.map_same[0];
+  } else {
+    const bool bits_only = conv1_uses_table(net) && p.input_ones && net->in_ch == 1;
+    p.map_conv1 = add_map(0, 0, net->conv1_ks, conv1_uses_table(net) && !bits_only);
+    p.maps[p.map_conv1].bits_only = bits_only;
+  }
   for (int i = 0; i < p.n_maps; ++i) {
     KMap& m = p.maps[i];
     const Level& Lin = p.lv[m.lin];
@@ -397,10 +407,11 @@ int32_t plan_begin(dgr_ctx* c, const dgr_net* net, Plan& p) {
                              m.meta, st));          // meta[0] = pairs P (for the roofline bookkeeping)
       continue;
     }
-    DGR_TRY(aalloc(c, (int64_t)m.K * dgr_kmap_mask_words(nmx), &m.bits));
+    m.W = dgr_kmap_mask_words(nmx);
+    DGR_TRY(aalloc(c, (int64_t)m.K * m.W, &m.bits));
     DGR_TRY(aalloc(c, dgr_kmap_cnt_elems(m.K, nmx), &m.cnt));
     DGR_TRY(aalloc(c, m.K + 2, &m.kofs));
-    const bool bloom = use_bloom && m.K > 27;
+    const bool bloom = Lin.bloom != nullptr && m.K > 27;
     DGR_TRY(dgr_kmap_probe(Lout.coords, Lout.n_max, Lout.n_dev, ncols, p.spec, Lin.keys, Lin.vals, Lin.cap,
                            bloom ? Lin.bloom : nullptr, bloom ? Lin.n_bloom : 0, m.offsets, m.K, m.bits, m.cnt, m.kofs,
                            m.meta, st));
@@ -416,9 +427,9 @@ int32_t plan_finish(dgr_ctx* c, Plan& p) {
   for (int i = 0; i < p.n_maps; ++i) {
     KMap& m = p.maps[i];
     const int32_t* mm = mh + 4 + kMetaPerMap * i;
-    if (m.dense) {
+    if (m.dense || m.bits_only) {
       m.P = mm[0];
-      m.nonempty = m.K;
+      m.nonempty = m.dense ? m.K : mm[3];
       continue;
     }
     m.P = mm[0]; m.n_tiles = mm[1]; m.n_ptiles = mm[2]; m.nonempty = mm[3];
@@ -454,6 +465,7 @@ struct LayerExec {
   int n_in, n_out;
   bool table;     // conv1: output-stationary fp32 table kernel (few input channels)
   bool os;        // output-stationary tensor-core kernel with the fused epilogue
+  bool bits;      // conv1 on an all-ones input from the occupancy masks
 };
 
 int tc_variant() {
@@ -473,8 +485,8 @@ bool tc_f16_enabled() {
 }
 bool tc_os_enabled() {
   static const bool v = [] {
-    const char* e = getenv("DGR_TC_OS");
-    return e ? atoi(e) != 0 : true;
+    const char* e = getenv("DGR_TC_OS");      // output-stationary kernel for the 3-D stride-1 layers: opt-in (measured
+    return e ? atoi(e) != 0 : false;          // slower than the pair-list kernel on B200)
   }();
   return v;
 }
@@ -501,7 +513,10 @@ int32_t run_conv(dgr_ctx* c, const LayerExec& L, const float* feat, const float*
     rec.bytes = (double)m.P * (cv.cin + cv.cout) * 4.0 + 8.0 * m.P + (double)m.nonempty * cv.cin * cv.cout * 4.0;
     cudaEventRecord(rec.e0, c->stream);
   }
-  if (L.table) {
+  if (L.bits) {
+    DGR_TRY(dgr_spconv_ones_bits_fwd(cv.w, cv.cout, m.bits, m.W, m.K, L.n_out, cv.scale, cv.shift, out, st));
+    rec.kind = 2;
+  } else if (L.table) {
     DGR_TRY(dgr_spconv_table_fwd_strided(feat, cv.cin, cv.w, cv.cout, m.nbr, m.K, L.n_out, m.nbr_stride, cv.scale,
                                          cv.shift, out, st));
     rec.kind = 2;
@@ -516,9 +531,14 @@ int32_t run_conv(dgr_ctx* c, const LayerExec& L, const float* feat, const float*
       if (cv.f16) {
         // |input| maximum -> the power-of-two activation scale of this launch (read on the device)
         float* amax;
-        DGR_TRY(aalloc(c, 1, &amax));
-        DGR_TRY(dgr_absmax_f32(feat, (int64_t)L.n_in * cv.cin, amax, st));
-        if (prof) cudaEventRecord(rec.e0, c->stream);      // the timed launch is the convolution itself
+        auto known = c->amax_of.find(feat);
+        if (known != c->amax_of.end()) {
+          amax = known->second;            // reduced by the elementwise pass that produced `feat`
+        } else {
+          DGR_TRY(aalloc(c, 1, &amax));
+          DGR_TRY(dgr_absmax_f32(feat, (int64_t)L.n_in * cv.cin, amax, st));
+          if (prof) cudaEventRecord(rec.e0, c->stream);      // the timed launch is the convolution itself
+        }
         DGR_TRY(dgr_spconv_tc_f16_fwd(feat, cv.cin, cv.packed16, cv.cout, in_idx, out_idx, m.kofs, m.ptile_k,
                                       m.ptile_start, m.n_ptiles, kTileRows, amax, cv.wscale, out, st));
         rec.kind = 0;
@@ -553,38 +573,49 @@ int32_t run_network(dgr_ctx* c, const dgr_net* net, Plan& p, const float* feats_
   const int n[4] = {p.lv[0].n, p.lv[1].n, p.lv[2].n, p.lv[3].n};
   for (int s = 0; s < 4; ++s) {
     const KMap* m = s == 0 ? &p.maps[p.map_conv1] : &p.maps[p.map_down[s - 1]];
-    const bool os = p.maps[p.map_same[s]].dense;
-    layers.push_back({&net->enc[s], m, false, s == 0 ? n[0] : n[s - 1], n[s], s == 0 && m->dense && m != &p.maps[p.map_same[0]], false});
-    layers.push_back({&net->eb1[s], &p.maps[p.map_same[s]], false, n[s], n[s], false, os});
-    layers.push_back({&net->eb2[s], &p.maps[p.map_same[s]], false, n[s], n[s], false, os});
+    const bool os = net->os_level[s];
+    layers.push_back({&net->enc[s], m, false, s == 0 ? n[0] : n[s - 1], n[s], s == 0 && m->dense && m != &p.maps[p.map_same[0]], false,
+                      s == 0 && m->bits_only});
+    layers.push_back({&net->eb1[s], &p.maps[p.map_same[s]], false, n[s], n[s], false, os, false});
+    layers.push_back({&net->eb2[s], &p.maps[p.map_same[s]], false, n[s], n[s], false, os, false});
   }
   for (int d = 0; d < 3; ++d) {
     const int lo = 2 - d;       // output level index
-    const bool os = p.maps[p.map_same[lo]].dense;
-    layers.push_back({&net->dec[d], &p.maps[p.map_down[lo]], true, n[lo + 1], n[lo], false, false});
-    layers.push_back({&net->db1[d], &p.maps[p.map_same[lo]], false, n[lo], n[lo], false, os});
-    layers.push_back({&net->db2[d], &p.maps[p.map_same[lo]], false, n[lo], n[lo], false, os});
+    const bool os = net->os_level[lo];
+    layers.push_back({&net->dec[d], &p.maps[p.map_down[lo]], true, n[lo + 1], n[lo], false, false, false});
+    layers.push_back({&net->db1[d], &p.maps[p.map_same[lo]], false, n[lo], n[lo], false, os, false});
+    layers.push_back({&net->db2[d], &p.maps[p.map_same[lo]], false, n[lo], n[lo], false, os, false});
   }
   // one slab for every convolution output, zero-filled once (the scatter-add kernels accumulate)
   // (output-stationary layers write every row themselves: their outputs live outside the zeroed slab)
   int64_t total = 0, total_os = 0;
-  for (auto& L : layers) (L.table || L.os ? total_os : total) += (int64_t)L.n_out * L.conv->cout;
+  for (auto& L : layers) (L.table || L.os || L.bits ? total_os : total) += (int64_t)L.n_out * L.conv->cout;
   float *slab, *slab_os;
   DGR_TRY(aalloc(c, total, &slab));
   DGR_TRY(aalloc(c, total_os, &slab_os));
   if (total > 0) DGR_CUDA_CHECK(cudaMemsetAsync(slab, 0, (size_t)total * sizeof(float), c->stream));
   int64_t ofs = 0, ofs_os = 0;
   auto take = [&](const LayerExec& L) {
-    const bool direct = L.table || L.os;
+    const bool direct = L.table || L.os || L.bits;
     float* b = direct ? slab_os + ofs_os : slab + ofs;
     (direct ? ofs_os : ofs) += (int64_t)L.n_out * L.conv->cout;
     return b;
   };
+  // max |activation| of every elementwise-pass output, reduced in that pass: the 3xFP16 layers read their
+  // input's slot instead of sweeping the tensor again
+  float* amax_slots;
+  DGR_TRY(aalloc(c, (int64_t)layers.size() + 1, &amax_slots));
+  DGR_CUDA_CHECK(cudaMemsetAsync(amax_slots, 0, (layers.size() + 1) * sizeof(float), c->stream));
+  int n_slots = 0;
+  c->amax_of.clear();
   auto conv_bn = [&](const LayerExec& L, const float* feat, const float* residual, int relu, float** res) -> int32_t {
     float* o = take(L);
     DGR_TRY(run_conv(c, L, feat, residual, relu, o));
-    if (!L.table && !L.os)
-      DGR_TRY(dgr_affine_act(o, L.n_out, L.conv->cout, L.conv->scale, L.conv->shift, residual, relu, o, st));
+    if (!L.table && !L.os && !L.bits) {
+      float* slot = (L.conv->cout % 4 == 0) ? amax_slots + n_slots++ : nullptr;
+      DGR_TRY(dgr_affine_act_amax(o, L.n_out, L.conv->cout, L.conv->scale, L.conv->shift, residual, relu, o, slot, st));
+      if (slot != nullptr) c->amax_of[o] = slot;
+    }
     *res = o;
     return DGR_OK;
   };
@@ -778,11 +809,12 @@ int32_t dgr_net_create(int32_t device, int32_t D, int32_t in_ch, int32_t out_ch,
   int k3 = 1, k1 = 1;
   for (int a = 0; a < D; ++a) { k3 *= 3; k1 *= conv1_ks; }
   int pi = 0;
-  auto set_conv = [&](Conv& cv, int cin, int cout, int ksize, int K) -> int32_t {
+  // os: a stride-1 3^3 layer of the 3-D network, run by the output-stationary kernel (3xTF32 slabs)
+  auto set_conv = [&](Conv& cv, int cin, int cout, int ksize, int K, bool os) -> int32_t {
     cv.w = params[pi++]; cv.scale = params[pi++]; cv.shift = params[pi++];
     cv.cin = cin; cv.cout = cout; cv.ksize = ksize; cv.K = K;
     cv.tc = dgr_spconv_tc_supported(cin, cout) != 0;
-    cv.f16 = cv.tc && tc_f16_enabled() && tc_variant() == 3 && cout >= tc_pair_min_cout() &&
+    cv.f16 = cv.tc && !os && tc_f16_enabled() && tc_variant() == 3 && cout >= tc_pair_min_cout() &&
              dgr_spconv_tc_f16_supported(cin, cout) != 0;
     if (cv.f16) {
       DGR_CUDA_CHECK(cudaMalloc(&cv.packed16, (size_t)4 * K * cin * cout));
@@ -798,18 +830,25 @@ int32_t dgr_net_create(int32_t device, int32_t D, int32_t in_ch, int32_t out_ch,
     return DGR_OK;
   };
   const int enc_in[4] = {in_ch, C[1], C[2], C[3]};
+  const int dec_lvl_ch[4] = {T[2], T[3], T[4], 0};      // decoder block channels at level 0, 1, 2 (none at level 3)
+  for (int l = 0; l < 4; ++l)
+    net->os_level[l] = D == 3 && tc_os_enabled() && !(l == 0 && conv1_ks == 3) &&
+                       dgr_spconv_os_supported(C[l + 1], C[l + 1]) &&
+                       (l == 3 || dgr_spconv_os_supported(dec_lvl_ch[l], dec_lvl_ch[l]));
   int32_t rc = DGR_OK;
   for (int s = 0; s < 4 && rc == DGR_OK; ++s) {
-    rc = set_conv(net->enc[s], enc_in[s], C[s + 1], s == 0 ? conv1_ks : 3, s == 0 ? k1 : k3);
-    if (rc == DGR_OK) rc = set_conv(net->eb1[s], C[s + 1], C[s + 1], 3, k3);
-    if (rc == DGR_OK) rc = set_conv(net->eb2[s], C[s + 1], C[s + 1], 3, k3);
+    const bool os = net->os_level[s];
+    rc = set_conv(net->enc[s], enc_in[s], C[s + 1], s == 0 ? conv1_ks : 3, s == 0 ? k1 : k3, false);
+    if (rc == DGR_OK) rc = set_conv(net->eb1[s], C[s + 1], C[s + 1], 3, k3, os);
+    if (rc == DGR_OK) rc = set_conv(net->eb2[s], C[s + 1], C[s + 1], 3, k3, os);
   }
   const int dec_in[3] = {C[4], C[3] + T[4], C[2] + T[3]};
   const int dec_out[3] = {T[4], T[3], T[2]};
   for (int d = 0; d < 3 && rc == DGR_OK; ++d) {
-    rc = set_conv(net->dec[d], dec_in[d], dec_out[d], 3, k3);
-    if (rc == DGR_OK) rc = set_conv(net->db1[d], dec_out[d], dec_out[d], 3, k3);
-    if (rc == DGR_OK) rc = set_conv(net->db2[d], dec_out[d], dec_out[d], 3, k3);
+    const bool os = net->os_level[2 - d];
+    rc = set_conv(net->dec[d], dec_in[d], dec_out[d], 3, k3, false);
+    if (rc == DGR_OK) rc = set_conv(net->db1[d], dec_out[d], dec_out[d], 3, k3, os);
+    if (rc == DGR_OK) rc = set_conv(net->db2[d], dec_out[d], dec_out[d], 3, k3, os);
   }
   if (rc != DGR_OK) {
     for (auto p : net->owned) cudaFree(p);
@@ -857,6 +896,7 @@ int32_t dgr_net_forward(dgr_ctx_t* c, dgr_net_t* net, const int32_t* coords, int
   p.lv[0].coords = const_cast<int32_t*>(coords);
   p.lv[0].n_max = n;
   p.lv[0].n = (int)n;
+  p.input_ones = feats == nullptr;
   DGR_TRY(plan_begin(c, net, p));
   DGR_TRY(read_meta(c, meta_ints(p)));
   DGR_TRY(plan_finish(c, p));
@@ -945,6 +985,7 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
   pf.lv[0].keys = keys;
   pf.lv[0].vals = vals;
   pf.lv[0].cap = cap;
+  pf.input_ones = true;
   DGR_TRY(plan_begin(c, fcgf, pf));
   mark_stage(c);                                        // 2: FCGF coordinate phase
   DGR_TRY(read_meta(c, meta_ints(pf)));                 // host read 1
@@ -997,6 +1038,7 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
   pi.lv[0].coords = coords6;
   pi.lv[0].n_max = N0;
   pi.lv[0].n = N0;
+  pi.input_ones = true;
   DGR_TRY(plan_begin(c, inlier, pi));
   mark_stage(c);                                        // 6: 6-D coordinate phase
   DGR_TRY(read_meta(c, meta_ints(pi)));                 // host read 2

@@ -18,6 +18,8 @@
 // product is off by at most 2^-10 |a||b| (+ accumulation slack), and d~2 by twice that.  The
 // true nearest neighbour j* satisfies d~2(j*) <= d2(j*) + E <= d2(j) + E <= d~2(j) + 2E for
 // every j, hence it is always among the candidates and the result equals the fp32 kernel's.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -65,14 +67,22 @@ __global__ void knn_tc_init_kernel(unsigned* __restrict__ rowmin_bits, unsigned 
   if (i == 0) *max_bits = 0u;
 }
 
-// thr_i = m~_i + 2 E_i with E_i = 2 * (dot-product error bound)
+// thr_i = m~_i + 2 E_i with E_i = 2 * (dot-product error bound).
+// coarse (one TF32 product): operands rounded to TF32, |a.b error| <= 2^-10 * 1.25 |a||b| (+ accumulation slack);
+// fine (3xTF32, hi*hi + lo*hi + hi*lo): the dropped lo*lo term and the truncation of the lo parts are each
+// <= 2^-22 |a||b|, fp32 accumulation of 32 products <= 32 * 2^-24 |a||b|: 4e-6 |a||b| covers them with margin.
+// Both add the slack of the fp32 norms.
+__device__ __forceinline__ float knn_error_bound(float na, float nb, bool fine) {
+  const float rel = fine ? 4e-6f : (0.0009765625f * 1.25f + 4e-5f);
+  return rel * na * nb + 1e-6f * (na + nb) * (na + nb) + 1e-7f;
+}
 __global__ void knn_tc_threshold_kernel(const unsigned* __restrict__ rowmin_bits, const float* __restrict__ na2,
-                                        const unsigned* __restrict__ nb2_max_bits, int64_t n0,
+                                        const unsigned* __restrict__ nb2_max_bits, int64_t n0, int fine,
                                         float* __restrict__ thr) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n0) return;
   const float na = sqrtf(na2[i]), nb = sqrtf(__uint_as_float(*nb2_max_bits));
-  const float e = (0.0009765625f * 1.25f + 4e-5f) * na * nb + 1e-6f * (na + nb) * (na + nb) + 1e-7f;
+  const float e = knn_error_bound(na, nb, fine != 0);
   // stored in the epilogue's units: candidates satisfy (0.5 |b|^2 - a.b) <= thr'
   thr[i] = 0.5f * (__uint_as_float(rowmin_bits[i]) + 4.f * e - na2[i]);
 }
@@ -89,6 +99,15 @@ __device__ __forceinline__ void round_store(float4 v, unsigned char* tile, int r
   float4 h;
   h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
   *reinterpret_cast<float4*>(tile + row * 128 + ((piece ^ (row & 7)) << 4)) = h;
+}
+
+__device__ __forceinline__ void split_store2(float4 v, unsigned char* hi_tile, unsigned char* lo_tile, int row, int piece) {
+  float4 h, l;
+  h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+  const int off = row * 128 + ((piece ^ (row & 7)) << 4);
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
 // exact reference arithmetic for one candidate column, as in knn.cu
@@ -131,19 +150,20 @@ __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int C, int PASS>
+template <int C, int PASS, bool kFine>
 __global__ void __launch_bounds__(kThreadsK, 1)
 knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1, int n1,
               const float* __restrict__ na2, const float* __restrict__ nb2, int cols_per_split,
               unsigned* __restrict__ rowmin_bits, const float* __restrict__ thr,
-              unsigned long long* __restrict__ packed) {
+              unsigned long long* __restrict__ packed, const unsigned* __restrict__ nb2_max_bits) {
   constexpr int kChunks = C / 32;
+  constexpr int kParts = kFine ? 2 : 1;            // operand tiles per chunk: TF32 hi (+ residual lo)
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   KnnShared& sh = *reinterpret_cast<KnnShared*>(smem_dyn);
   unsigned char* a_tile = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + sizeof(KnnShared) + 1023) & ~(uintptr_t)1023);
-  unsigned char* b_stage0 = a_tile + kChunks * kATile;
-  constexpr int kStageBytes = kChunks * kBTile;
+  unsigned char* b_stage0 = a_tile + kParts * kChunks * kATile;
+  constexpr int kStageBytes = kParts * kChunks * kBTile;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int row0 = blockIdx.x * kRowsA;
   const int col_begin = blockIdx.y * cols_per_split;
@@ -183,7 +203,8 @@ knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1
         const int r = i * 16 + rgrp;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row0 + r < n0) v = __ldg(reinterpret_cast<const float4*>(f0 + (size_t)(row0 + r) * C + ch * 32 + piece * 4));
-        round_store(v, a_tile + ch * kATile, r, piece);
+        if (kFine) split_store2(v, a_tile + (2 * ch) * kATile, a_tile + (2 * ch + 1) * kATile, r, piece);
+        else round_store(v, a_tile + ch * kATile, r, piece);
       }
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it & 1;
@@ -208,7 +229,10 @@ knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1
 #pragma unroll
       for (int ch = 0; ch < kChunks; ++ch)
 #pragma unroll
-        for (int i = 0; i < kColsB / 16; ++i) round_store(bv[ch][i], b_tile + ch * kBTile, i * 16 + rgrp, piece);
+        for (int i = 0; i < kColsB / 16; ++i) {
+          if (kFine) split_store2(bv[ch][i], b_tile + (2 * ch) * kBTile, b_tile + (2 * ch + 1) * kBTile, i * 16 + rgrp, piece);
+          else round_store(bv[ch][i], b_tile + ch * kBTile, i * 16 + rgrp, piece);
+        }
       sh.nb[s][t] = 0.5f * nb_a;          // the epilogue works with 0.5 |b|^2 - a.b
       sh.nb[s][128 + t] = 0.5f * nb_b;
       fence_proxy_async();
@@ -230,9 +254,19 @@ knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1
 #pragma unroll
         for (int ch = 0; ch < kChunks; ++ch)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc_mma_tf32(tmem_base + (uint32_t)s * kColsB, umma_desc(a0 + ch * kATile + ks * 32),
-                        umma_desc(b0 + ch * kBTile + ks * 32), idesc, (ch | ks) != 0);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t td = tmem_base + (uint32_t)s * kColsB;
+            if (kFine) {
+              const uint64_t ah = umma_desc(a0 + (2 * ch) * kATile + ks * 32), al = umma_desc(a0 + (2 * ch + 1) * kATile + ks * 32);
+              const uint64_t bh = umma_desc(b0 + (2 * ch) * kBTile + ks * 32), bl = umma_desc(b0 + (2 * ch + 1) * kBTile + ks * 32);
+              tc_mma_tf32(td, ah, bh, idesc, (ch | ks) != 0);
+              tc_mma_tf32(td, al, bh, idesc, 1);
+              tc_mma_tf32(td, ah, bl, idesc, 1);
+            } else {
+              tc_mma_tf32(td, umma_desc(a0 + ch * kATile + ks * 32), umma_desc(b0 + ch * kBTile + ks * 32), idesc,
+                          (ch | ks) != 0);
+            }
+          }
         tc_commit(smem_u32(&sh.acc_full[s]));
       }
       __syncwarp();
@@ -244,7 +278,13 @@ knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1
     const int r = lane_grp * 32 + lane;
     const int gi = row0 + r;
     const bool valid = gi < n0;
-    const float th = (PASS == 2 && valid) ? thr[gi] : -__int_as_float(0x7f800000);
+    float th = (PASS == 2 && valid) ? thr[gi] : -__int_as_float(0x7f800000);
+    // pass 2 tightens its bound with every exact distance it learns: a later column can only win if its true
+    // d2 is below the best exact d2 so far, i.e. if its estimate is below best_d2 + (estimate error)
+    const float na2_i = (PASS == 2 && valid) ? na2[gi] : 0.f;
+    const float e4 = (PASS == 2 && valid)
+                         ? 4.f * knn_error_bound(sqrtf(na2_i), sqrtf(__uint_as_float(*nb2_max_bits)), kFine)
+                         : 0.f;
     float rmin = __int_as_float(0x7f800000);     // min over columns of 0.5 |b|^2 - a.b
     float best_s = __int_as_float(0x7f800000), best_d2 = best_s;
     int best_j = 0x7fffffff;
@@ -278,7 +318,10 @@ knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1
 #pragma unroll
               for (int q = 0; q < 32; ++q) {
                 const float g = hb[cc * 32 + q] - __uint_as_float(cur[q]);
-                if (g <= th) knn_exact_candidate<C>(f0, f1, gi, jc + q, best_s, best_d2, best_j);
+                if (g <= th) {
+                  knn_exact_candidate<C>(f0, f1, gi, jc + q, best_s, best_d2, best_j);
+                  th = fminf(th, 0.5f * (best_d2 + e4 - na2_i));
+                }
               }
             }
           } else {
@@ -287,7 +330,10 @@ knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1
               const float g = hb[cc * 32 + q] - __uint_as_float(cur[q]);
               if (jc + q < col_end) {
                 if (PASS == 1) rmin = fminf(rmin, g);
-                else if (g <= th) knn_exact_candidate<C>(f0, f1, gi, jc + q, best_s, best_d2, best_j);
+                else if (g <= th) {
+                  knn_exact_candidate<C>(f0, f1, gi, jc + q, best_s, best_d2, best_j);
+                  th = fminf(th, 0.5f * (best_d2 + e4 - na2_i));
+                }
               }
             }
           }
@@ -320,14 +366,15 @@ __global__ void knn_tc_unpack_kernel(const unsigned long long* __restrict__ pack
   if (dist != nullptr) dist[i] = __uint_as_float((unsigned)(p >> 32));
 }
 
-template <int C>
+template <int C, bool kFine>
 int32_t launch_knn_tc(const float* f0, int64_t n0, const float* f1, int64_t n1, float* na2, float* nb2,
                       unsigned* rowmin, float* thr, unsigned* max_bits, unsigned long long* packed,
                       cudaStream_t st) {
   constexpr int kChunks = C / 32;
-  const size_t smem = sizeof(KnnShared) + 1024 + (size_t)kChunks * kATile + 2 * (size_t)kChunks * kBTile;
-  DGR_ENSURE_SMEM((knn_tc_kernel<C, 1>), smem);
-  DGR_ENSURE_SMEM((knn_tc_kernel<C, 2>), smem);
+  constexpr int kParts = kFine ? 2 : 1;
+  const size_t smem = sizeof(KnnShared) + 1024 + (size_t)kParts * kChunks * kATile + 2 * (size_t)kParts * kChunks * kBTile;
+  DGR_ENSURE_SMEM((knn_tc_kernel<C, 1, kFine>), smem);
+  DGR_ENSURE_SMEM((knn_tc_kernel<C, 2, kFine>), smem);
   const int row_tiles = (int)((n0 + kRowsA - 1) / kRowsA);
   const int col_tiles = (int)((n1 + kColsB - 1) / kColsB);
   int splits = (148 * 4 + row_tiles - 1) / row_tiles;
@@ -336,11 +383,11 @@ int32_t launch_knn_tc(const float* f0, int64_t n0, const float* f1, int64_t n1, 
   const int cols_per_split = ((col_tiles + splits - 1) / splits) * kColsB;
   splits = (int)((n1 + cols_per_split - 1) / cols_per_split);
   dim3 grid(row_tiles, splits);
-  knn_tc_kernel<C, 1><<<grid, kThreadsK, smem, st>>>(f0, (int)n0, f1, (int)n1, na2, nb2, cols_per_split,
-                                                     rowmin, thr, packed);
-  knn_tc_threshold_kernel<<<dgr_blocks(n0, 256), 256, 0, st>>>(rowmin, na2, max_bits, n0, thr);
-  knn_tc_kernel<C, 2><<<grid, kThreadsK, smem, st>>>(f0, (int)n0, f1, (int)n1, na2, nb2, cols_per_split,
-                                                     rowmin, thr, packed);
+  knn_tc_kernel<C, 1, kFine><<<grid, kThreadsK, smem, st>>>(f0, (int)n0, f1, (int)n1, na2, nb2, cols_per_split,
+                                                            rowmin, thr, packed, max_bits);
+  knn_tc_threshold_kernel<<<dgr_blocks(n0, 256), 256, 0, st>>>(rowmin, na2, max_bits, n0, kFine ? 1 : 0, thr);
+  knn_tc_kernel<C, 2, kFine><<<grid, kThreadsK, smem, st>>>(f0, (int)n0, f1, (int)n1, na2, nb2, cols_per_split,
+                                                            rowmin, thr, packed, max_bits);
   return DGR_OK;
 }
 
@@ -372,8 +419,12 @@ int32_t dgr_knn_top1_tc(const float* f0, int64_t n0, const float* f1, int64_t n1
   knn_tc_init_kernel<<<dgr_blocks(n0, 256), 256, 0, st>>>(rowmin, packed, n0, max_bits);
   row_norms_kernel<<<dgr_blocks(n0 * 8, 256), 256, 0, st>>>(f0, n0, c, na2, nullptr);
   row_norms_kernel<<<dgr_blocks(n1 * 8, 256), 256, 0, st>>>(f1, n1, c, nb2, max_bits);
-  int32_t rc = (c == 32) ? launch_knn_tc<32>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st)
-                         : launch_knn_tc<64>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st);
+  // c = 32 (the FCGF dimension): 3xTF32 products, a ~150x narrower candidate band; c = 64: single TF32 product
+  // (the hi + lo tiles of two 256-column stages would not fit shared memory)
+  static const bool coarse = getenv("DGR_KNN_COARSE") != nullptr;      // A/B switch
+  int32_t rc = (c == 32) ? (coarse ? launch_knn_tc<32, false>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st)
+                                   : launch_knn_tc<32, true>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st))
+                         : launch_knn_tc<64, false>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st);
   if (rc != DGR_OK) return rc;
   knn_tc_unpack_kernel<<<dgr_blocks(n0, 256), 256, 0, st>>>(packed, n0, idx, dist);
   dgr_note_launches(7);

@@ -306,30 +306,93 @@ spconv_table_kernel(const float* __restrict__ in_feat, int cin, const float* __r
   }
 }
 
+// conv1 of the FCGF network on its actual input: ONE input channel whose value is 1 for every voxel
+// (core/deep_global_registration.py:96,159: `feats = ones`).  Then out[j, :] = sum over the occupied offsets
+// kappa of W[kappa, 0, :]: only the OCCUPANCY of the 7^3 neighbourhood matters, not which row sits there - the
+// kernel reads the kernel map's bit masks (bits[kappa][j / 32], one word per warp and offset, broadcast) instead of
+// a dense 343 x N index table: 32x less traffic, and the map needs neither pair lists nor a neighbour table.
+template <int COUT>
+__global__ void __launch_bounds__(kThreads)
+spconv_ones_bits_kernel(const float* __restrict__ weight, const uint32_t* __restrict__ bits, int W, int K, int64_t n_out,
+                        const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out) {
+  extern __shared__ __align__(16) float w_s[];   // [kc, COUT] chunk of the weights
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = (int)(j >> 5), lane = threadIdx.x & 31;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  const int kc_max = (44 * 1024 / 4) / COUT;
+  for (int k0 = 0; k0 < K; k0 += kc_max) {
+    const int kn = min(kc_max, K - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kn * COUT; e += blockDim.x) w_s[e] = weight[(int64_t)k0 * COUT + e];
+    __syncthreads();
+    if (w < W) {
+      for (int kb = 0; kb < kn; kb += 8) {
+        uint32_t m[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m[u] = (kb + u < kn) ? __ldg(bits + (int64_t)(k0 + kb + u) * W + w) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (!((m[u] >> lane) & 1u)) continue;
+          const float4* wr = reinterpret_cast<const float4*>(w_s + (kb + u) * COUT);
+#pragma unroll
+          for (int c4 = 0; c4 < COUT / 4; ++c4) {
+            const float4 wv = wr[c4];
+            acc[4 * c4 + 0] += wv.x; acc[4 * c4 + 1] += wv.y; acc[4 * c4 + 2] += wv.z; acc[4 * c4 + 3] += wv.w;
+          }
+        }
+      }
+    }
+  }
+  if (j >= n_out) return;
+  float4* dst = reinterpret_cast<float4*>(out + j * COUT);
+#pragma unroll
+  for (int c4 = 0; c4 < COUT / 4; ++c4) {
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      v[c] = acc[4 * c4 + c];
+      if (scale != nullptr) v[c] = v[c] * scale[4 * c4 + c] + shift[4 * c4 + c];
+    }
+    dst[c4] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // elementwise
 // ---------------------------------------------------------------------------------------
+// amax (optional): receives max |out| as float bits (atomicMax on non-negative floats) - the activation scale the
+// 3xFP16 convolution that consumes `out` needs, for free in the pass that produces it
 __global__ void affine_act_kernel(const float* __restrict__ x, int64_t total, int c,
                                   const float* __restrict__ scale, const float* __restrict__ shift,
-                                  const float* __restrict__ residual, int relu, float* out) {
+                                  const float* __restrict__ residual, int relu, float* out, unsigned* amax) {
   // c % 4 == 0: one float4 per thread
-  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= total) return;
-  int ch = (int)(i % c);
-  float4 v = *reinterpret_cast<const float4*>(x + i);
-  if (scale != nullptr) {
-    float4 s = *reinterpret_cast<const float4*>(scale + ch);
-    float4 b = *reinterpret_cast<const float4*>(shift + ch);
-    v.x = v.x * s.x + b.x; v.y = v.y * s.y + b.y; v.z = v.z * s.z + b.z; v.w = v.w * s.w + b.w;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  float m = 0.f;
+  if (i < total) {
+    const int ch = (int)(i % c);
+    float4 v = *reinterpret_cast<const float4*>(x + i);
+    if (scale != nullptr) {
+      const float4 s = *reinterpret_cast<const float4*>(scale + ch);
+      const float4 b = *reinterpret_cast<const float4*>(shift + ch);
+      v.x = v.x * s.x + b.x; v.y = v.y * s.y + b.y; v.z = v.z * s.z + b.z; v.w = v.w * s.w + b.w;
+    }
+    if (residual != nullptr) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + i);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(out + i) = v;
+    m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
   }
-  if (residual != nullptr) {
-    float4 r = *reinterpret_cast<const float4*>(residual + i);
-    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  if (amax != nullptr) {               // uniform branch: every lane of the warp takes part in the shuffles
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
   }
-  if (relu) {
-    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-  }
-  *reinterpret_cast<float4*>(out + i) = v;
 }
 
 __global__ void affine_act_scalar_kernel(const float* __restrict__ x, int64_t total, int c,
@@ -488,6 +551,32 @@ int32_t dgr_spconv_table_fwd(const float* in_feat, int32_t cin, const float* wei
   return dgr_spconv_table_fwd_strided(in_feat, cin, weight, cout, nbr, K, n_out, n_out, scale, shift, out, stream);
 }
 
+// conv1 with one all-ones input channel from the kernel map's occupancy masks (dgr_kmap_probe's `bits`):
+//   out[j, :] = (sum over kappa with bit (kappa, j) set of weight[kappa, 0, :]) * scale + shift.
+// Same summation order over kappa as dgr_spconv_table_fwd on an all-ones input (bit-identical result).
+int32_t dgr_spconv_ones_bits_fwd(const float* weight, int32_t cout, const uint32_t* bits, int64_t mask_words, int32_t K,
+                                 int64_t n_out, const float* scale, const float* shift, float* out, void* stream) {
+  DGR_ARG_CHECK((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+  DGR_ARG_CHECK(mask_words * 32 >= n_out, "mask rows shorter than the output");
+  if (n_out == 0) return DGR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = 44 * 1024;
+  const unsigned blocks = dgr_blocks(n_out, kThreads);
+  if (cout == 32)
+    spconv_ones_bits_kernel<32><<<blocks, kThreads, smem, st>>>(weight, bits, (int)mask_words, K, n_out, scale, shift, out);
+  else if (cout == 64)
+    spconv_ones_bits_kernel<64><<<blocks, kThreads, smem, st>>>(weight, bits, (int)mask_words, K, n_out, scale, shift, out);
+  else if (cout == 16)
+    spconv_ones_bits_kernel<16><<<blocks, kThreads, smem, st>>>(weight, bits, (int)mask_words, K, n_out, scale, shift, out);
+  else {
+    dgr_set_error("dgr_spconv_ones_bits_fwd: cout must be 16, 32 or 64 (got %d)", cout);
+    return DGR_ERR_ARG;
+  }
+  dgr_note_launches(1);
+  DGR_LAUNCH_CHECK();
+  return DGR_OK;
+}
+
 int32_t dgr_linear_fwd(const float* a, int32_t ca, const float* b, int32_t cb, int64_t n,
                        const float* weight, int32_t cout, const float* bias, int32_t relu,
                        int32_t normalize, float* out, void* stream) {
@@ -507,21 +596,29 @@ int32_t dgr_linear_fwd(const float* a, int32_t ca, const float* b, int32_t cb, i
   return DGR_OK;
 }
 
-int32_t dgr_affine_act(const float* x, int64_t n, int32_t c, const float* scale, const float* shift,
-                       const float* residual, int32_t relu, float* out, void* stream) {
+// dgr_affine_act that also reduces max |out| into amax[0] (device float; the CALLER zeroes it, so that several
+// launches may reduce into one slot); requires c % 4 == 0 when amax is given.
+int32_t dgr_affine_act_amax(const float* x, int64_t n, int32_t c, const float* scale, const float* shift,
+                            const float* residual, int32_t relu, float* out, float* amax, void* stream) {
   DGR_ARG_CHECK((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+  DGR_ARG_CHECK(amax == nullptr || c % 4 == 0, "amax needs a channel count divisible by 4");
   const int64_t total = n * c;
   if (total == 0) return DGR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (c % 4 == 0)
-    affine_act_kernel<<<dgr_blocks(total / 4, kThreads), kThreads, 0, st>>>(x, total, c, scale, shift,
-                                                                          residual, relu, out);
+    affine_act_kernel<<<dgr_blocks(total / 4, kThreads), kThreads, 0, st>>>(x, total, c, scale, shift, residual, relu,
+                                                                          out, reinterpret_cast<unsigned*>(amax));
   else
     affine_act_scalar_kernel<<<dgr_blocks(total, kThreads), kThreads, 0, st>>>(x, total, c, scale, shift,
                                                                              residual, relu, out);
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;
+}
+
+int32_t dgr_affine_act(const float* x, int64_t n, int32_t c, const float* scale, const float* shift,
+                       const float* residual, int32_t relu, float* out, void* stream) {
+  return dgr_affine_act_amax(x, n, c, scale, shift, residual, relu, out, nullptr, stream);
 }
 
 int32_t dgr_cat2(const float* a, int32_t ca, const float* b, int32_t cb, int64_t n, float* out,

@@ -289,6 +289,10 @@ int32_t dgr_spconv_wgrad(const float* in_feat, int32_t cin, const float* grad_ou
  * fp16 has TF32's 11 significant bits at half the bytes and twice the tensor rate; operands are scaled by
  * powers of two (exact) so that the tensor's absolute maximum lands in [2^14, 2^15), then split hi / lo as
  * in the 3xTF32 path: same 2^-21 relative accuracy, 1.5 TF32-MMA equivalents per product instead of 3. */
+/* dgr_affine_act that also reduces max |out| into amax[0] (device float, zeroed by the CALLER): the activation
+ * scale of the 3xFP16 convolution consuming `out`, computed in the pass that produces it. */
+int32_t dgr_affine_act_amax(const float* x, int64_t n, int32_t c, const float* scale, const float* shift,
+                            const float* residual, int32_t relu, float* out, float* amax, void* stream);
 /* amax[0] (device float, zeroed by the call) = max |x[i]|. */
 int32_t dgr_absmax_f32(const float* x, int64_t n, float* amax, void* stream);
 int32_t dgr_spconv_tc_f16_supported(int32_t cin, int32_t cout);     /* cin % 64 == 0, cout % 32 == 0, <= 256 */
@@ -302,6 +306,12 @@ int32_t dgr_spconv_tc_f16_fwd(const float* in_feat, int32_t cin, const void* wei
                               const int32_t* in_idx, const int32_t* out_idx, const int32_t* kofs,
                               const int32_t* tile_k, const int32_t* tile_start, int32_t n_tiles, int32_t tile_rows,
                               const float* amax_in, const float* w_scale, float* out, void* stream);
+
+/* conv1 of the FCGF network on its actual input - one channel, all ones (core/deep_global_registration.py:96,159)
+ * - from the kernel map's occupancy masks (bits[K][mask_words] of dgr_kmap_probe) instead of a dense 343 x N
+ * neighbour table: out[j, :] = (sum over kappa with bit (kappa, j) set of weight[kappa, 0, :]) * scale + shift. */
+int32_t dgr_spconv_ones_bits_fwd(const float* weight, int32_t cout, const uint32_t* bits, int64_t mask_words, int32_t K,
+                                 int64_t n_out, const float* scale, const float* shift, float* out, void* stream);
 
 /* ---- coordinate planning without host round trips (csrc/coordplan.cu) --------------------
  * Convention: `n_max` is a host-side upper bound of a row count (sizes buffers and grids), `n_dev` a
@@ -329,7 +339,7 @@ int32_t dgr_coarse_maps(const int32_t* fine, int64_t n_max, const int32_t* n_dev
 /* Blocked Bloom filter of a table (both bits of a key in one 32-bit word); n_words a power of two. */
 int32_t dgr_bloom2_build(const uint64_t* keys, int64_t cap, uint32_t* words, int64_t n_words, void* stream);
 /* Kernel map, phase 1: bits[K][W] (W = dgr_kmap_mask_words(n_out_max)) holds one bit per (offset, output row),
- * block_cnt (dgr_kmap_cnt_elems ints) the exclusive-scanned per-(offset, 2048-word block) pair counts,
+ * block_cnt (dgr_kmap_cnt_elems ints) the exclusive-scanned per-(offset, 256-word block) pair counts,
  * kofs[K + 2] the bucket offsets + key-overflow flag, meta[5] = (pairs P, 128-row tiles, tiles with an even
  * count per offset, non-empty offsets, key overflow).  bloom_words (optional, <= 32768 words) is copied to
  * shared memory and answers most misses there.  No host synchronisation. */

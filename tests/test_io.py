@@ -116,6 +116,11 @@ def test_trajectory_round_trip(tmp_path):
     dio.read_trajectory(tmp_path / 'bad.log')
 
 
+def torch_cuda_available():
+  import torch
+  return torch.cuda.is_available()
+
+
 def test_open3d_stand_in(tmp_path, cloud, monkeypatch):
   from deepglobalregistration_b200 import shims
   try:
@@ -138,4 +143,15 @@ def test_open3d_stand_in(tmp_path, cloud, monkeypatch):
   o3d.visualization.draw_geometries([pcd, q])
   assert o3d.io.write_point_cloud(str(tmp_path / 'b.ply'), q)
   assert np.array_equal(dio.read_ply(tmp_path / 'b.ply')[0], cloud[:10])
-  assert not hasattr(o3d, 'pipelines')        # registration is never routed through the stand-in
+  # round 2: the registration pipeline the reference's own class calls is part of the stand-in (GPU-backed; the
+  # calls themselves are exercised in tests/test_gpu_reference_on_shim.py)
+  reg = o3d.pipelines.registration
+  assert o3d.registration is reg and callable(reg.registration_icp) and \
+      callable(reg.registration_ransac_based_on_correspondence)
+  crit = reg.RANSACConvergenceCriteria(4000000, 80000)           # core/deep_global_registration.py:62
+  assert crit.max_iteration == 4000000 and crit.confidence == 1.0
+  assert reg.ICPConvergenceCriteria().max_iteration == 30
+  assert o3d.utility.Vector2iVector(np.zeros((5, 2))).shape == (5, 2)
+  if not torch_cuda_available():
+    with pytest.raises(Exception):                                 # no CPU fallback
+      reg.registration_icp(pcd, q, 0.1)
