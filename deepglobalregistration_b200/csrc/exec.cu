@@ -608,11 +608,12 @@ int32_t run_network(dgr_ctx* c, const dgr_net* net, Plan& p, const float* feats_
   DGR_CUDA_CHECK(cudaMemsetAsync(amax_slots, 0, (layers.size() + 1) * sizeof(float), c->stream));
   int n_slots = 0;
   c->amax_of.clear();
-  auto conv_bn = [&](const LayerExec& L, const float* feat, const float* residual, int relu, float** res) -> int32_t {
+  auto conv_bn = [&](const LayerExec& L, const float* feat, const float* residual, int relu, bool want_amax,
+                     float** res) -> int32_t {
     float* o = take(L);
     DGR_TRY(run_conv(c, L, feat, residual, relu, o));
     if (!L.table && !L.os && !L.bits) {
-      float* slot = (L.conv->cout % 4 == 0) ? amax_slots + n_slots++ : nullptr;
+      float* slot = (want_amax && L.conv->cout % 4 == 0) ? amax_slots + n_slots++ : nullptr;
       DGR_TRY(dgr_affine_act_amax(o, L.n_out, L.conv->cout, L.conv->scale, L.conv->shift, residual, relu, o, slot, st));
       if (slot != nullptr) c->amax_of[o] = slot;
     }
@@ -624,9 +625,11 @@ int32_t run_network(dgr_ctx* c, const dgr_net* net, Plan& p, const float* feats_
   size_t li = 0;
   for (int stage = 0; stage < 7; ++stage) {
     float *a, *h, *b;
-    DGR_TRY(conv_bn(layers[li], feat, nullptr, 0, &a));
-    DGR_TRY(conv_bn(layers[li + 1], a, nullptr, 1, &h));
-    DGR_TRY(conv_bn(layers[li + 2], h, a, 1, &b));
+    // an output's maximum is reduced in its elementwise pass only when a 3xFP16 layer consumes it
+    const bool next_f16 = stage < 6 && stage != 4 && stage != 5 && li + 3 < layers.size() && layers[li + 3].conv->f16;
+    DGR_TRY(conv_bn(layers[li], feat, nullptr, 0, layers[li + 1].conv->f16, &a));
+    DGR_TRY(conv_bn(layers[li + 1], a, nullptr, 1, layers[li + 2].conv->f16, &h));
+    DGR_TRY(conv_bn(layers[li + 2], h, a, 1, next_f16, &b));
     const int n_rows = layers[li + 2].n_out, ch = layers[li + 2].conv->cout;
     li += 3;
     feat = b;

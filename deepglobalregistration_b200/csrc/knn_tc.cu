@@ -5,10 +5,11 @@
 //
 //   pass 1  D = F0_tile . F1_tile^T on the tensor cores (TF32, accumulator in TMEM);
 //           the epilogue (thread = F0 row = TMEM lane) forms d~2 = |a|^2 + |b|^2 - 2 D and
-//           keeps the row minimum m~_i - over every 8th column tile only (round 2): any upper
-//           bound of the true minimum keeps the candidate set a superset, and the minimum of a
-//           1/8 sample is exceeded by ~8 columns on average, so pass 2 evaluates a handful more
-//           candidates per row while pass 1 costs an eighth of a full sweep;
+//           keeps the row minimum m~_i.  (Round 2 measured a pass 1 over every 8th column tile - any
+//           upper bound of the minimum keeps the candidate set a superset: pass 1 fell from 0.55 to
+//           0.09 ms but pass 2 grew from 0.91 to 1.68 ms on the looser bound; and 3xTF32 products
+//           (kFine, a ~150x narrower band) cost more in operand staging than they save: 2.0 ms.
+//           The full single-product sweep stays.)
 //   pass 2  the same products again; every column with d~2 <= m~_i + 2 E_i is a CANDIDATE and
 //           only candidates are evaluated with the reference arithmetic
 //           (fp32 sum_c (a - b)^2 in ascending c, sqrt(d2 + 1e-7), lowest index on ties) - the
@@ -36,7 +37,7 @@ constexpr int kRowsA = 128;
 constexpr int kColsB = 256;
 constexpr int kATile = kRowsA * 128;    // bytes per 32-float chunk
 constexpr int kBTile = kColsB * 128;
-constexpr int kPass1Stride = 8;        // pass 1 looks at every 8th column tile
+constexpr int kPass1Stride = 1;        // pass 1 column-tile stride (a sampled pass 1 was measured: see header)
 
 __global__ void row_norms_kernel(const float* __restrict__ f, int64_t n, int c, float* __restrict__ n2,
                                  unsigned* __restrict__ max_bits) {
@@ -419,9 +420,9 @@ int32_t dgr_knn_top1_tc(const float* f0, int64_t n0, const float* f1, int64_t n1
   knn_tc_init_kernel<<<dgr_blocks(n0, 256), 256, 0, st>>>(rowmin, packed, n0, max_bits);
   row_norms_kernel<<<dgr_blocks(n0 * 8, 256), 256, 0, st>>>(f0, n0, c, na2, nullptr);
   row_norms_kernel<<<dgr_blocks(n1 * 8, 256), 256, 0, st>>>(f1, n1, c, nb2, max_bits);
-  // c = 32 (the FCGF dimension): 3xTF32 products, a ~150x narrower candidate band; c = 64: single TF32 product
-  // (the hi + lo tiles of two 256-column stages would not fit shared memory)
-  static const bool coarse = getenv("DGR_KNN_COARSE") != nullptr;      // A/B switch
+  // default: single TF32 product per term.  DGR_KNN_FINE=1 (c = 32 only): 3xTF32 products, a ~150x narrower
+  // candidate band, measured slower (the hi + lo tiles double the operand staging)
+  static const bool coarse = getenv("DGR_KNN_FINE") == nullptr;        // A/B switch: 3xTF32 pre-filter (slower)
   int32_t rc = (c == 32) ? (coarse ? launch_knn_tc<32, false>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st)
                                    : launch_knn_tc<32, true>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st))
                          : launch_knn_tc<64, false>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st);

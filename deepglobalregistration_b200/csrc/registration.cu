@@ -468,7 +468,16 @@ icp_match_kernel(const float* __restrict__ src, int64_t n_src, const float* __re
 #pragma unroll
   for (int k = 0; k < 17; ++k) acc[k] = 0.0;
   const int reach = (int)ceil(max_dist / voxel);     // cells to search on every side (2 for DGR)
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += (int64_t)gridDim.x * blockDim.x) {
+  const int side = 2 * reach + 1, n_cells = side * side * side;
+  // 8 lanes share one source point: the (2 reach + 1)^3 = 125 candidate cells are probed 8 at a time (a thread
+  // per point walked them serially - 125 dependent L2 round trips - and left the SMs 92 % idle), then the lanes'
+  // best (d2, then lower row) is reduced with shuffles; lane 0 of the group accumulates the moments
+  const int sub = threadIdx.x & 7;
+  const int64_t groups = ((int64_t)gridDim.x * blockDim.x) >> 3;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i0 < ((n_src + groups - 1) / groups) * groups;
+       i0 += groups) {
+    const bool have = i0 < n_src;                      // whole warps stay in the loop for the shuffles
+    const int64_t i = have ? i0 : 0;
     const double x = src[3 * i], y = src[3 * i + 1], z = src[3 * i + 2];
     const double p[3] = {T[0] * x + T[1] * y + T[2] * z + T[3], T[4] * x + T[5] * y + T[6] * z + T[7],
                          T[8] * x + T[9] * y + T[10] * z + T[11]};
@@ -477,28 +486,36 @@ icp_match_kernel(const float* __restrict__ src, int64_t n_src, const float* __re
     for (int a = 0; a < 3; ++a) cell[a] = (int)floor(p[a] / voxel);
     double best = max_dist * max_dist;
     int best_j = -1;
-    for (int dz = -reach; dz <= reach; ++dz)
-      for (int dy = -reach; dy <= reach; ++dy)
-        for (int dx = -reach; dx <= reach; ++dx) {
-          const int32_t row[4] = {batch, cell[0] + dx, cell[1] + dy, cell[2] + dz};
-          bool inside = true;
+    for (int c = sub; c < n_cells && have; c += 8) {
+      const int dx = c % side - reach, dy = (c / side) % side - reach, dz = c / (side * side) - reach;
+      const int32_t row[4] = {batch, cell[0] + dx, cell[1] + dy, cell[2] + dz};
+      bool inside = true;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const long long d = (long long)row[c] - s.lo[c];
-            inside = inside && d >= 0 && d < (1ll << s.bits[c]);
-          }
-          if (!inside) continue;
-          const int32_t j = dgr_hash_lookup(keys, vals, mask, dgr_pack_key(row, s));
-          if (j < 0) continue;
-          const double ex = p[0] - tgt[3 * (int64_t)j], ey = p[1] - tgt[3 * (int64_t)j + 1],
-                       ez = p[2] - tgt[3 * (int64_t)j + 2];
-          const double d2 = ex * ex + ey * ey + ez * ez;
-          if (d2 < best || (d2 == best && best_j >= 0 && j < best_j) || (d2 == best && best_j < 0)) {
-            best = d2;
-            best_j = j;
-          }
-        }
-    if (best_j >= 0) {
+      for (int q = 0; q < 4; ++q) {
+        const long long d = (long long)row[q] - s.lo[q];
+        inside = inside && d >= 0 && d < (1ll << s.bits[q]);
+      }
+      if (!inside) continue;
+      const int32_t j = dgr_hash_lookup(keys, vals, mask, dgr_pack_key(row, s));
+      if (j < 0) continue;
+      const double ex = p[0] - tgt[3 * (int64_t)j], ey = p[1] - tgt[3 * (int64_t)j + 1],
+                   ez = p[2] - tgt[3 * (int64_t)j + 2];
+      const double d2 = ex * ex + ey * ey + ez * ez;
+      if (d2 < best || (d2 == best && (best_j < 0 || j < best_j))) {
+        best = d2;
+        best_j = j;
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {                  // nearest, lower row index on ties: order-independent
+      const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j, d);
+      if (oj >= 0 && (best_j < 0 || ob < best || (ob == best && oj < best_j))) {
+        best = ob;
+        best_j = oj;
+      }
+    }
+    if (have && sub == 0 && best_j >= 0) {
       const double q[3] = {tgt[3 * (int64_t)best_j], tgt[3 * (int64_t)best_j + 1], tgt[3 * (int64_t)best_j + 2]};
       acc[0] += 1.0;
       acc[1] += best;
@@ -641,8 +658,8 @@ int32_t dgr_icp_point_to_point(const float* src, int64_t n_src, const float* tgt
   cudaStream_t st = (cudaStream_t)stream;
   IcpState* state = reinterpret_cast<IcpState*>(state_ws);
   icp_init_kernel<<<1, 32, 0, st>>>(T_init, state);
-  unsigned blocks = dgr_blocks(n_src, 256);
-  if (blocks > 1184) blocks = 1184;
+  unsigned blocks = dgr_blocks(n_src * 8, 256);      // 8 lanes per source point
+  if (blocks > 2368) blocks = 2368;
   for (int k = 0; k <= max_iter; ++k) {
     icp_match_kernel<<<blocks, 256, 0, st>>>(src, n_src, tgt, spec, keys, vals, (uint64_t)cap - 1, batch, voxel,
                                              max_dist, state);

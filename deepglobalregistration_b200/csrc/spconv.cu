@@ -388,10 +388,19 @@ __global__ void affine_act_kernel(const float* __restrict__ x, int64_t total, in
     *reinterpret_cast<float4*>(out + i) = v;
     m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
   }
-  if (amax != nullptr) {               // uniform branch: every lane of the warp takes part in the shuffles
+  if (amax != nullptr) {               // uniform branch: every thread of the block takes part
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+    __shared__ float wmax[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, wmax[w]);
+      // one same-address atomic per BLOCK at most, and only from blocks that raise the slot (a plain read
+      // filters the rest: same-address atomics serialise at L2)
+      if (__float_as_uint(m) > *reinterpret_cast<volatile unsigned*>(amax)) atomicMax(amax, __float_as_uint(m));
+    }
   }
 }
 
