@@ -44,7 +44,7 @@ REF_TIME_BUDGET_S = 240       # --impl reference: stop starting full-size pairs 
 REF_MIN_N_RAW = 1500          # the reference arm's untimed warm-up sample
 VOXEL = 0.05
 POOL = 3                      # distinct pairs per rank, cycled over the steps
-INFLIGHT = int(os.environ.get('DGR_BENCH_INFLIGHT', '3'))   # pairs in flight per GPU (pipeline pairs per GPU)
+INFLIGHT = int(os.environ.get('DGR_BENCH_INFLIGHT', '4'))   # pairs in flight per GPU (pipeline pairs per GPU)
 
 
 _emit = print

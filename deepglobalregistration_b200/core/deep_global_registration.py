@@ -296,7 +296,7 @@ class DeepGlobalRegistration:
     self._log(f'=> DGR takes {t:.2} s' if branch == 'procrustes' else f'=> Safeguard takes {t:.2} s')
     return T
 
-  def register_batch(self, pairs, inflight=3):
+  def register_batch(self, pairs, inflight=4):
     """Register independent pairs with `inflight` of them in flight on this GPU (one host thread, stream
     and arena each): the latency-bound stages and host reads of one pair overlap the convolutions
     of the other.  pairs: [(xyz0, xyz1), ...] (arrays, tensors, point clouds, or callables returning such a

@@ -31,6 +31,8 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges show up in Nsight Systems / ncu --nvtx, no-ops otherwise
+
 #include "common.cuh"
 
 namespace {
@@ -264,7 +266,23 @@ cudaEvent_t pool_event(dgr_ctx* c) {
   return e;
 }
 
-void mark_stage(dgr_ctx* c) {
+const char* const kStageNames[] = {"dgr:upload+voxelise", "dgr:fcgf_coordinate_phase", "dgr:read1+fcgf_pair_lists",
+                                   "dgr:fcgf_convolutions", "dgr:feature_knn", "dgr:inlier_coordinate_phase",
+                                   "dgr:read2+inlier_pair_lists", "dgr:inlier_convolutions",
+                                   "dgr:weights+procrustes+refine(+icp)"};
+
+// stage boundary k of dgr_pair_register (0 = start ... 9 = end): NVTX range per stage, CUDA event when profiling
+struct StageRanges {             // closes the open NVTX range on every exit path of dgr_pair_register
+  bool open = false;
+  ~StageRanges() {
+    if (open) nvtxRangePop();
+  }
+};
+
+void mark_stage(dgr_ctx* c, StageRanges& r, int k) {
+  if (r.open) nvtxRangePop();
+  r.open = k < 9;
+  if (r.open) nvtxRangePushA(kStageNames[k]);
   if (!c->profile) return;
   cudaEvent_t e = pool_event(c);
   cudaEventRecord(e, c->stream);
@@ -936,7 +954,8 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
   const int64_t n_raw = n_raw0 + n_raw1;
   for (auto e : c->stage_marks) c->event_pool.push_back(e);
   c->stage_marks.clear();
-  mark_stage(c);                                        // 0: start
+  StageRanges ranges;
+  mark_stage(c, ranges, 0);                                // 0: start
 
   // ---- stage 0: upload + voxelise both scans into ONE batched coordinate set (batch 0 / 1) -------------
   const void *d0 = xyz0, *d1 = xyz1;
@@ -976,7 +995,7 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
   DGR_TRY(dgr_compact_voxel_pair(raw, sel, n_unique, n_raw0, n_raw1, d0, is_f64_0, d1, is_f64_1, coords, xyz,
                                  c->meta_dev, st));
 
-  mark_stage(c);                                        // 1: upload + voxelisation enqueued
+  mark_stage(c, ranges, 1);                                        // 1: upload + voxelisation enqueued
   // ---- stage 1: FCGF features of both clouds in one forward pass ------------------------------------------
   Plan pf;
   pf.D = 3;
@@ -990,7 +1009,7 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
   pf.lv[0].cap = cap;
   pf.input_ones = true;
   DGR_TRY(plan_begin(c, fcgf, pf));
-  mark_stage(c);                                        // 2: FCGF coordinate phase
+  mark_stage(c, ranges, 2);                                        // 2: FCGF coordinate phase
   DGR_TRY(read_meta(c, meta_ints(pf)));                 // host read 1
   const int N = c->meta_host[0], N0 = c->meta_host[1], N1 = c->meta_host[2];
   if (c->meta_host[3] != 0) {
@@ -1003,13 +1022,13 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
   }
   pf.lv[0].n = N;
   DGR_TRY(plan_finish(c, pf));
-  mark_stage(c);                                        // 3: FCGF pair lists + work lists
+  mark_stage(c, ranges, 3);                                        // 3: FCGF pair lists + work lists
   float *ones, *F;
   DGR_TRY(ones_features(c, N, &ones));
   const int Cf = fcgf->out_ch;
   DGR_TRY(aalloc(c, (int64_t)N * Cf, &F));
   DGR_TRY(run_network(c, fcgf, pf, ones, F));
-  mark_stage(c);                                        // 4: FCGF convolution phase
+  mark_stage(c, ranges, 4);                                        // 4: FCGF convolution phase
 
   // ---- stage 2: feature nearest neighbour (core/knn.py:23-74) --------------------------------------------
   int32_t* idx1;
@@ -1024,7 +1043,7 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
     DGR_TRY(dgr_knn_top1(F, N0, F + (int64_t)N0 * Cf, N1, Cf, packed_ws, idx1, nullptr, st));
   }
 
-  mark_stage(c);                                        // 5: feature kNN
+  mark_stage(c, ranges, 5);                                        // 5: feature kNN
   // ---- stage 3/4: 6-D coordinates and the inlier network ---------------------------------------------------
   int32_t *coords6, *minmax6;
   dgr_keyspec_t* spec6;
@@ -1043,16 +1062,16 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
   pi.lv[0].n = N0;
   pi.input_ones = true;
   DGR_TRY(plan_begin(c, inlier, pi));
-  mark_stage(c);                                        // 6: 6-D coordinate phase
+  mark_stage(c, ranges, 6);                                        // 6: 6-D coordinate phase
   DGR_TRY(read_meta(c, meta_ints(pi)));                 // host read 2
   DGR_TRY(plan_finish(c, pi));
-  mark_stage(c);                                        // 7: 6-D pair lists + work lists
+  mark_stage(c, ranges, 7);                                        // 7: 6-D pair lists + work lists
   float *ones6, *logit, *w;
   DGR_TRY(ones_features(c, N0, &ones6));
   DGR_TRY(aalloc(c, N0, &logit));
   DGR_TRY(aalloc(c, N0, &w));
   DGR_TRY(run_network(c, inlier, pi, ones6, logit));
-  mark_stage(c);                                        // 8: inlier convolution phase
+  mark_stage(c, ranges, 8);                                        // 8: inlier convolution phase
 
   // ---- stage 5: weights, gate sum, weighted Procrustes + SE(3) refinement, ICP ---------------------------
   double *wsum, *icp_res = nullptr;
@@ -1077,7 +1096,7 @@ int32_t dgr_pair_register(dgr_ctx_t* c, dgr_net_t* fcgf, dgr_net_t* inlier, cons
     DGR_TRY(dgr_icp_point_to_point(xyz, N0, xyz, spec, keys, vals, cap, 1, voxel, 2 * voxel, T12, 30, 1e-6, 1e-6,
                                    state, icp_res, st));
   }
-  mark_stage(c);                                        // 9: weights + Procrustes + refinement (+ ICP)
+  mark_stage(c, ranges, 9);                                        // 9: weights + Procrustes + refinement (+ ICP)
   pack_result_kernel<<<1, 64, 0, c->stream>>>(se3, wsum, icp_res, c->res_dev);
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();

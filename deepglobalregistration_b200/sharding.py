@@ -62,7 +62,7 @@ def _cloud(item):
   return item
 
 
-def register_pairs(dgr, pairs, device=None, inflight=3):
+def register_pairs(dgr, pairs, device=None, inflight=4):
   """Register this rank's share of `pairs` ([(xyz0, xyz1), ...]; members may be file paths) with
   `dgr` and gather all results.  Returns [len(pairs), 20] float64, identical on every rank.  With a
   DeepGlobalRegistration that has register_batch, `inflight` pairs are kept in flight on the GPU (one host

@@ -21,7 +21,7 @@ def main(path):
   hdr, units, data = rows[0], rows[1], rows[2:]
   idx = {h: i for i, h in enumerate(hdr)}
   print('# ' + ' '.join(sys.argv))
-  print('# units: time ' + units[idx['gpu__time_duration.sum']] + ', dram bytes ' + units[idx['dram__bytes_read.sum']] +
+  print('# units: time ms, dram bytes ' + units[idx['dram__bytes_read.sum']] +
         '; cold-cache, serialised launches (compare shares, not absolutes)')
   print('kernel'.ljust(44) + ' '.join(n.rjust(10) for _, n, _ in COLS))
   for r in data:
@@ -29,7 +29,10 @@ def main(path):
     vals = []
     for key, _, _ in COLS:
       try:
-        vals.append('%.4g' % float(r[idx[key]].replace(',', '')))
+        v = float(r[idx[key]].replace(',', ''))
+        if key == 'gpu__time_duration.sum':      # ncu picks a unit per file: normalise to milliseconds
+          v *= {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}.get(units[idx[key]], 1.0)
+        vals.append('%.4g' % v)
       except Exception:   # noqa: BLE001
         vals.append('-')
     print(name.ljust(44) + ' '.join(v.rjust(10) for v in vals))
