@@ -5,7 +5,9 @@
   config 5  stress: room-type cloud scaled to ~1M voxels at 0.02 m, FCGF out = 64: voxelisation,
             hash / kernel-map construction, FCGF forward and feature kNN, sweep over N.
 
-Writes gpurun_out/configs_r01.json."""
+Round 2: config 3 goes through the native executor (one C call per pair); config 5 additionally runs the FCGF
+forward through dgr_net_forward (device-side counts, bit-mask kernel maps) at every size and compares it with the
+operator path.  Writes gpurun_out/configs_r02.json."""
 import json
 import os
 import sys
@@ -16,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from deepglobalregistration_b200 import _abi, me as ME, synthetic as syn
+from deepglobalregistration_b200 import _abi, me as ME, native, synthetic as syn
 from deepglobalregistration_b200.core.deep_global_registration import DeepGlobalRegistration
 from deepglobalregistration_b200.model import load_model
 
@@ -51,11 +53,12 @@ def config5():
   model = load_model('ResUNetBN2C')(1, 64, bn_momentum=0.05, conv1_kernel_size=7, normalize_feature=True)
   model.load_state_dict(syn.resunet_state_dict(0, 1, 64, 7, 3))
   model = model.cuda().eval()
+  net, ctx = native.Net(model, 'cuda'), native.Context('cuda')
   full = syn.room_scan(0, n_raw=3_000_000, extent=(9.0, 7.5, 3.0))
   for frac in (1 / 16, 1 / 4, 1.0):
     xyz = full[:int(len(full) * frac)]
     d = torch.from_numpy(xyz).cuda()
-    rec = {}
+    rec, native_ms, native_err = {}, None, None
     for rep in range(3):
       torch.cuda.synchronize()
       e0 = ev()
@@ -74,10 +77,18 @@ def config5():
         e3 = ev()
       torch.cuda.synchronize()
       pairs = sum(km.n_pairs for _, _, km, _ in layers)
+      if rep == 2:       # the same forward pass through the native executor (one C call, one host read)
+        Fn = net.forward(ctx, coords)
+        t0 = time.perf_counter()
+        Fn = net.forward(ctx, coords)
+        native_ms = (time.perf_counter() - t0) * 1e3
+        native_err = float((Fn - F).abs().max())
+        del Fn
       rec = dict(n_raw=len(xyz), n_voxels=n, voxelise_ms=e0.elapsed_time(e1),
                  voxelise_GBps=len(xyz) * (24 + 16 + 12) / e0.elapsed_time(e1) / 1e6,
                  kernel_maps_ms=e1.elapsed_time(e2), fcgf_convs_ms=e2.elapsed_time(e3),
-                 kernel_map_pairs_total=int(pairs))
+                 kernel_map_pairs_total=int(pairs), native_forward_ms_incl_maps=native_ms,
+                 native_vs_operator_path_max_abs=native_err, native_arena_bytes=ctx.stats()['arena_high_water'])
     # kNN of the cloud against itself shifted (same size): N x N x 64
     if n <= 300_000:
       F1 = F.roll(1, 0).contiguous()
@@ -106,5 +117,5 @@ def config5():
 if __name__ == '__main__':
   res = dict(config3_kitti_shape_register=config3(), config5_stress_sweep=config5())
   os.makedirs('gpurun_out', exist_ok=True)
-  json.dump(res, open('gpurun_out/configs_r01.json', 'w'), indent=1)
+  json.dump(res, open('gpurun_out/configs_r02.json', 'w'), indent=1)
   print(json.dumps(res, indent=1))
