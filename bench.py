@@ -391,8 +391,8 @@ def run_ours(args):
     e0.record()
     out = dgr.register_batch(pairs, inflight=inflight)
     rows = [sharding.pack_result(T, info.get('wsum', 0.0), info.get('iterations', 0), branch) for T, branch, info in out]
-    if strong:
-      gathered = gather_poses(rows, args.pairs)
+    if strong and n_steps == len(seeds):
+      gathered = gather_poses(rows, args.pairs)            # the whole fixed set, in pair order
     else:
       gathered = gather_poses(rows, world * len(rows))
     e1.record()
