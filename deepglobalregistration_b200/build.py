@@ -18,6 +18,7 @@ OBJ_DIR = os.path.join(HERE, 'build')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-I', INCLUDE, '-I', CSRC]
+NVCC_FLAGS += os.environ.get('DGR_EXTRA_NVCC_FLAGS', '').split()      # A/B build switches (e.g. -DDGR_GATHER_CG)
 
 
 def _nvcc():

@@ -32,6 +32,14 @@ namespace {
 
 using namespace tc;
 
+// gathered feature rows: ld.global.nc (default) or, with -DDGR_GATHER_CG, ld.global.cg (L2 only, no L1 allocation) -
+// an A/B build switch kept for the record in profiles/r02_experiments.txt
+#ifdef DGR_GATHER_CG
+#define DGR_GATHER_LOAD(p) __ldcg(p)
+#else
+#define DGR_GATHER_LOAD(p) __ldg(p)
+#endif
+
 #define DGR_TRY_RC(expr)             \
   do {                              \
     int32_t rc__ = (expr);          \
@@ -242,7 +250,7 @@ spconv_tc_kernel(const float* __restrict__ in_feat, int cin, const float* __rest
     auto load_a = [&](const int (&src)[4], int c, float4 (&v)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        v[i] = src[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)src[i] * cin + c * kChunk +
+        v[i] = src[i] >= 0 ? DGR_GATHER_LOAD(reinterpret_cast<const float4*>(in_feat + (size_t)src[i] * cin + c * kChunk +
                                                                     piece * 4))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
     };
@@ -747,7 +755,7 @@ spconv_tc_pair_kernel(const float* __restrict__ in_feat, int cin, const float* _
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int u = 0; u < kV; ++u)
-          v[i][u] = src[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(in_feat + (size_t)src[i] * cin + c * kCh +
+          v[i][u] = src[i] >= 0 ? DGR_GATHER_LOAD(reinterpret_cast<const float4*>(in_feat + (size_t)src[i] * cin + c * kCh +
                                                                          piece * (4 * kV) + 4 * u))
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
     };
