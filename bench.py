@@ -63,7 +63,7 @@ def base_config(n_gpus):
           'parallelism': f'pair-sharded dp{n_gpus}', 'pairs_per_step_per_gpu': 1,
           'excluded_on_both_arms': 'ICP fine-tune and RANSAC safeguard (both built; the benchmarked unit is SURVEY 8(d)\'s: through the SE(3) refinement, and the benchmark pairs take the Procrustes branch)',
           'l2_policy': 'inputs larger than L2: every step streams the 944 MB inlier-net weights '
-                       '(L2 = 126 MB) and cycles through %d distinct pairs' % POOL}
+                       '(L2 = 126 MB) and cycles through %d distinct pairs (the same ones on every rank)' % POOL}
 
 
 # ------------------------------------------------------------------------------------------
@@ -362,8 +362,10 @@ def run_ours(args):
     seeds = sharding.shard_indices(args.pairs, rank, world)
     n_steps_default = len(seeds)
   else:
-    # this rank's pairs (seeds disjoint across ranks), cycled over the steps: weak scaling
-    seeds = [1000 * rank + i for i in range(POOL)]
+    # weak scaling = the per-GPU work is FIXED as N grows: every rank registers the same POOL pairs (its own
+    # copies), cycled over the steps.  (Round 1 gave every rank its own seeds; their voxel counts differ by up to
+    # 10 %, and with the result gather as a sync point the slowest rank's data then set the 8-GPU time.)
+    seeds = list(range(POOL))
     n_steps_default = args.steps
   pool = min(len(seeds), POOL) if not strong else len(seeds)
   log(f'[bench] rank {rank}/{world}: generating {pool} pair(s)')

@@ -47,6 +47,7 @@ SIGNATURES = {
     'dgr_kernel_map_count': [_p, _i32, _i64, _p, _i32, _p, _p, _p],
     'dgr_kernel_map_fill': [_p, _i32, _i64, _p, _p, _p, _p],
     'dgr_kernel_map_tiles': [_p, _i32, _i32, _i32, _i32, _p, _p, _p],
+    'dgr_kernel_map_tiles2': [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
     'dgr_spconv_fwd': [_p, _i32, _p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p],
     'dgr_spconv_tc_supported': [_i32, _i32],
     'dgr_pack_weight_tf32': [_p, _i32, _i32, _i32, _p, _p],

@@ -376,8 +376,16 @@ __global__ void kernel_map_fill_kernel(const int32_t* __restrict__ nbr, int64_t 
   }
 }
 
+// gridDim.x == 2: block 0 writes the plain list, block 1 the paired one (both work lists of a map in one launch)
 __global__ void tiles_kernel(const int32_t* __restrict__ kofs, int K, int tile_rows, int n_tiles, int pair,
-                             int32_t* __restrict__ tile_k, int32_t* __restrict__ tile_start) {
+                             int32_t* __restrict__ tile_k, int32_t* __restrict__ tile_start, int n_tiles_b = 0,
+                             int32_t* __restrict__ tile_k_b = nullptr, int32_t* __restrict__ tile_start_b = nullptr) {
+  if (blockIdx.x == 1) {
+    pair = 1;
+    n_tiles = n_tiles_b;
+    tile_k = tile_k_b;
+    tile_start = tile_start_b;
+  }
   extern __shared__ int tofs[];   // K + 1 exclusive tile offsets
   __shared__ int wsum[32];
   __shared__ int carry_s;
@@ -598,6 +606,18 @@ int32_t dgr_kernel_map_fill(const int32_t* nbr, int32_t K, int64_t n_out, const 
   const unsigned bpk = dgr_blocks(n_out, kScanElems);
   kernel_map_fill_kernel<<<dim3(bpk, K), kThreads, 0, (cudaStream_t)stream>>>(nbr, n_out, block_ws,
                                                                             in_idx, out_idx);
+  dgr_note_launches(1);
+  DGR_LAUNCH_CHECK();
+  return DGR_OK;
+}
+
+// Both work lists of a kernel map (plain, and with an even tile count per offset) in one launch.
+int32_t dgr_kernel_map_tiles2(const int32_t* kofs, int32_t K, int32_t tile_rows, int32_t n_tiles, int32_t n_tiles_paired,
+                              int32_t* tile_k, int32_t* tile_start, int32_t* ptile_k, int32_t* ptile_start, void* stream) {
+  DGR_ARG_CHECK(tile_rows >= 1, "tile_rows must be positive");
+  if (n_tiles == 0 && n_tiles_paired == 0) return DGR_OK;
+  tiles_kernel<<<2, 1024, (K + 1) * sizeof(int), (cudaStream_t)stream>>>(kofs, K, tile_rows, n_tiles, 0, tile_k, tile_start,
+                                                                        n_tiles_paired, ptile_k, ptile_start);
   dgr_note_launches(1);
   DGR_LAUNCH_CHECK();
   return DGR_OK;

@@ -466,8 +466,8 @@ int32_t plan_finish(dgr_ctx* c, Plan& p) {
     if (m.P > 0) {
       DGR_TRY(dgr_kmap_fill(m.bits, m.cnt, m.K, Lout.n_max > 0 ? Lout.n_max : 1, Lout.coords, p.ncols, p.spec, Lin.keys,
                             Lin.vals, Lin.cap, m.offsets, m.in_idx, m.out_idx, st));
-      DGR_TRY(dgr_kernel_map_tiles(m.kofs, m.K, kTileRows, m.n_tiles, 0, m.tile_k, m.tile_start, st));
-      DGR_TRY(dgr_kernel_map_tiles(m.kofs, m.K, kTileRows, m.n_ptiles, 1, m.ptile_k, m.ptile_start, st));
+      DGR_TRY(dgr_kernel_map_tiles2(m.kofs, m.K, kTileRows, m.n_tiles, m.n_ptiles, m.tile_k, m.tile_start, m.ptile_k,
+                                    m.ptile_start, st));
     }
   }
   return DGR_OK;

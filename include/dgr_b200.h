@@ -138,6 +138,9 @@ int32_t dgr_kernel_map_fill(const int32_t* nbr, int32_t K, int64_t n_out, const 
  * cluster variant of the tensor-core convolution consumes. */
 int32_t dgr_kernel_map_tiles(const int32_t* kofs, int32_t K, int32_t tile_rows, int32_t n_tiles, int32_t pair,
                              int32_t* tile_k, int32_t* tile_start, void* stream);
+/* Both lists (pair = 0 and pair = 1) in one launch. */
+int32_t dgr_kernel_map_tiles2(const int32_t* kofs, int32_t K, int32_t tile_rows, int32_t n_tiles, int32_t n_tiles_paired,
+                              int32_t* tile_k, int32_t* tile_start, int32_t* ptile_k, int32_t* ptile_start, void* stream);
 
 /* ---- sparse convolution forward: ME.MinkowskiConvolution / ConvolutionTranspose
  *      (model/residual_block.py:38-44,72-80; graph model/resunet.py:598-649) ---------- */
