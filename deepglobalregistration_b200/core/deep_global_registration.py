@@ -220,7 +220,9 @@ class DeepGlobalRegistration:
   # native path: the whole pair in one C call (three host reads), see csrc/exec.cu
   # ---------------------------------------------------------------------------------------
   def _param_version(self):
-    return tuple(p._version for m in (self.fcgf_model, self.inlier_model) for p in list(m.parameters()) + list(m.buffers()))
+    # in-place updates bump _version; .to() / re-assignment changes the storage address the native table points at
+    return tuple((p._version, p.data_ptr()) for m in (self.fcgf_model, self.inlier_model)
+                 for p in list(m.parameters()) + list(m.buffers()))
 
   def native_networks(self):
     """(fcgf, inlier) native layer tables, rebuilt when a parameter or BatchNorm statistic changed."""

@@ -1,0 +1,6 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+(timeout 600 python -m pytest tests/test_gpu_executor.py tests/test_gpu_zzzz_golden_fullsize.py -x -q 2>&1 | tail -5) > gpurun_out/r_pytest.log 2>&1
+(timeout 400 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r_bench_1gpu.json) 2> gpurun_out/r_bench_1gpu.err
+tail -n 3 gpurun_out/r_pytest.log gpurun_out/r_bench_1gpu.err
