@@ -117,3 +117,42 @@ def test_reference_model_files_import_against_the_shim():
     for k in [k for k in sys.modules if k == 'model' or k.startswith('model.')]:
       del sys.modules[k]
     sys.modules.update(saved)
+
+
+def test_native_layer_table_parameter_order():
+  """native.network_parameters lists the 66 tensors dgr_net_create documents, in execution order, for this
+  package's ResUNetBN2C - and for the reference's own class over the shim when the reference tree is present
+  (same attribute names, model/resunet.py:442-596)."""
+  from deepglobalregistration_b200 import native, synthetic as syn
+  from deepglobalregistration_b200.model import load_model
+  models = [load_model('ResUNetBN2C')(1, 32, bn_momentum=0.05, conv1_kernel_size=7, normalize_feature=True, D=3)]
+  if os.path.isdir('/root/reference/model'):
+    from deepglobalregistration_b200 import shims
+    saved = {k: v for k, v in sys.modules.items() if k == 'model' or k.startswith('model.')}
+    for k in saved:
+      del sys.modules[k]
+    shims.install()
+    sys.path.insert(0, '/root/reference')
+    try:
+      from model.resunet import ResUNetBN2C as RefNet
+      models.append(RefNet(1, 32, bn_momentum=0.05, conv1_kernel_size=7, normalize_feature=True, D=3))
+    finally:
+      sys.path.remove('/root/reference')
+      for k in [k for k in sys.modules if k == 'model' or k.startswith('model.')]:
+        del sys.modules[k]
+      sys.modules.update(saved)
+  C, T = [None, 32, 64, 128, 256], [None, 64, 64, 64, 128]
+  for m in models:
+    m.load_state_dict(syn.resunet_state_dict(0, 1, 32, 7, 3))
+    m.eval()
+    ps = native.network_parameters(m)
+    assert len(ps) == 66 and all(p.dtype == torch.float32 and p.is_contiguous() for p in ps)
+    assert tuple(ps[0].shape) == (343, 1, 32) and tuple(ps[1].shape) == (32,) and tuple(ps[2].shape) == (32,)
+    assert tuple(ps[3].shape) == (27, 32, 32)                       # block1.conv1
+    assert tuple(ps[9].shape) == (27, C[1], C[2])                   # conv2 (stride 2)
+    assert tuple(ps[36].shape) == (27, C[4], T[4])                  # conv4_tr
+    assert tuple(ps[45].shape) == (27, C[3] + T[4], T[3])           # conv3_tr reads cat(decoder, skip)
+    assert tuple(ps[63].shape) == (C[1] + T[2], T[1]) and tuple(ps[64].shape) == (T[1], 32) and tuple(ps[65].shape) == (32,)
+    # folded BatchNorm: scale = weight / sqrt(var + eps)
+    bn = m.norm1.bn
+    assert torch.allclose(ps[1], bn.weight / torch.sqrt(bn.running_var + bn.eps))

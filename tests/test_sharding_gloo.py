@@ -63,3 +63,43 @@ def test_two_rank_gloo_all_gather(tmp_path):
     assert r0[i, 16].item() == 9.0 * i                    # wsum
     assert r0[i, 17].item() == 10 + i                     # iterations
     assert r0[i, 18].item() == (0.0 if i % 2 == 0 else 1.0)
+
+
+class _FakeBatchDgr(_FakeDgr):
+  """A registrar with the round-2 batch API: register_pairs hands it lazily produced pairs (callables) and keeps
+  the results in input order whatever order the in-flight pairs complete in."""
+
+  def register_batch(self, pairs, inflight=4):
+    import threading
+    import time
+    out = [None] * len(pairs)
+
+    def work(k):
+      for i in range(k, len(pairs), inflight):
+        a, b = pairs[i]() if callable(pairs[i]) else pairs[i]
+        time.sleep(0.001 * ((7 * i) % 5))                  # completion order differs from input order
+        d = _FakeDgr()
+        T = d.register(a, b)
+        out[i] = (T, d.last_branch, dict(d.last_info, t_done=time.perf_counter()))
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(inflight)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    return out
+
+
+def _worker_batch(rank, world, port, n_pairs, out_dir):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  res = sharding.register_pairs(_FakeBatchDgr(), _pairs(n_pairs), inflight=3)
+  torch.save(res, os.path.join(out_dir, f'b{rank}.pt'))
+  dist.destroy_process_group()
+
+
+def test_batch_api_two_ranks_keep_pair_order(tmp_path):
+  n_pairs, world = 11, 2
+  mp.spawn(_worker_batch, args=(world, _free_port(), n_pairs, str(tmp_path)), nprocs=world, join=True)
+  r0, r1 = torch.load(tmp_path / 'b0.pt'), torch.load(tmp_path / 'b1.pt')
+  assert torch.equal(r0[:, :19], r1[:, :19]) and r0.shape == (n_pairs, 20)
+  for i in range(n_pairs):
+    assert r0[i, 3].item() == i + 2 * (10 + i) and r0[i, 16].item() == 9.0 * i and r0[i, 17].item() == 10 + i
+  assert bool((r0[:, 19] >= 0).all())                      # milliseconds between completions on the owning rank
