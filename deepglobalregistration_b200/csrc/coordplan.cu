@@ -477,31 +477,16 @@ kmap_fill_kernel(const uint32_t* __restrict__ bits, int W, int bpk, const int32_
   const int32_t* o = offsets + (int64_t)kappa * (ncols - 1);
   for (int a = 0; a < ncols - 1; ++a) d += (long long)o[a] * (1ll << s.shift[a + 1]);
   const int w_first = blockIdx.x * kCntWords + warp * 32;      // this warp resolves its own 32 words
-  // four words per step: their coordinate loads and hash lookups are independent chains (a word at a time left
-  // each warp waiting on ~3 dependent L2 round trips per step, 32 steps in a row at the dense levels)
-  for (int u = 0; u < 32; u += 4) {
-    bool act[4];
-    int pos[4];
-    int64_t j[4];
-    uint64_t qq[4];
-    int32_t found[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t m = s_mask[warp * 32 + u + k];
-      act[k] = (m >> lane) & 1u;
-      j[k] = (int64_t)(w_first + u + k) * 32 + lane;
-      pos[k] = s_base[warp * 32 + u + k] + __popc(m & ((1u << lane) - 1u));
+  for (int u = 0; u < 32; ++u) {
+    const uint32_t m = s_mask[warp * 32 + u];
+    if (m == 0u) continue;                                     // uniform
+    if ((m >> lane) & 1u) {
+      const int64_t j = (int64_t)(w_first + u) * 32 + lane;
+      const int pos = s_base[warp * 32 + u] + __popc(m & ((1u << lane) - 1u));
+      const uint64_t qq = dgr_pack_key(out_coords + j * ncols, s) + (uint64_t)d;
+      in_idx[pos] = dgr_hash_lookup(keys, vals, mask, qq);
+      out_idx[pos] = (int32_t)j;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) qq[k] = act[k] ? dgr_pack_key(out_coords + j[k] * ncols, s) + (uint64_t)d : 0ull;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) found[k] = act[k] ? dgr_hash_lookup(keys, vals, mask, qq[k]) : -1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (act[k]) {
-        in_idx[pos[k]] = found[k];
-        out_idx[pos[k]] = (int32_t)j[k];
-      }
   }
 }
 
