@@ -9,7 +9,9 @@
 //           upper bound of the minimum keeps the candidate set a superset: pass 1 fell from 0.55 to
 //           0.09 ms but pass 2 grew from 0.91 to 1.68 ms on the looser bound; and 3xTF32 products
 //           (kFine, a ~150x narrower band) cost more in operand staging than they save: 2.0 ms.
-//           The full single-product sweep stays.)
+//           The full single-product sweep stays.  A SINGLE sweep with a running bound and a candidate buffer
+//           (PASS 3 below, DGR_KNN_SWEEPS=1) is bit-identical too but measured 6.6 ms against 1.5 ms on the
+//           benchmark's tightly clustered random-init features: profiles/r02_experiments.txt.)
 //   pass 2  the same products again; every column with d~2 <= m~_i + 2 E_i is a CANDIDATE and
 //           only candidates are evaluated with the reference arithmetic
 //           (fp32 sum_c (a - b)^2 in ascending c, sqrt(d2 + 1e-7), lowest index on ties) - the
@@ -37,6 +39,9 @@ constexpr int kRowsA = 128;
 constexpr int kColsB = 256;
 constexpr int kATile = kRowsA * 128;    // bytes per 32-float chunk
 constexpr int kBTile = kColsB * 128;
+constexpr int kCandCap = 16;           // single-sweep mode: buffered candidates per (row, column half)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr size_t kCandBytes = (size_t)2 * kCandCap * kEpiThreads * 4;   // column index + estimate
 constexpr int kPass1Stride = 1;        // pass 1 column-tile stride (a sampled pass 1 was measured: see header)
 
 __global__ void row_norms_kernel(const float* __restrict__ f, int64_t n, int c, float* __restrict__ n2,
@@ -134,6 +139,31 @@ __device__ __noinline__ void knn_exact_candidate(const float* __restrict__ f0, c
       best_j = j;
     }
   }
+}
+
+// the same arithmetic for candidates met in ANY order (single-sweep mode evaluates its buffered candidates after
+// the sweep, overflowed ones during it): smallest sqrt distance, lowest index among equal ones - what the ascending
+// walk above yields.  best_d2 is the smallest exact d2 seen; it only tightens the candidate bound.
+template <int C>
+__device__ __noinline__ void knn_exact_candidate_unordered(const float* __restrict__ f0, const float* __restrict__ f1,
+                                                           int gi, int j, float& best_s, float& best_d2, int& best_j) {
+  const float4* a = reinterpret_cast<const float4*>(f0 + (size_t)gi * C);
+  const float4* b = reinterpret_cast<const float4*>(f1 + (size_t)j * C);
+  float d2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < C / 4; ++k) {
+    const float4 x = __ldg(a + k), y = __ldg(b + k);
+    float df = x.x - y.x; d2 = fmaf(df, df, d2);
+    df = x.y - y.y; d2 = fmaf(df, df, d2);
+    df = x.z - y.z; d2 = fmaf(df, df, d2);
+    df = x.w - y.w; d2 = fmaf(df, df, d2);
+  }
+  const float sq = sqrtf(d2 + 1e-7f);
+  if (sq < best_s || (sq == best_s && j < best_j)) {
+    best_s = sq;
+    best_j = j;
+  }
+  best_d2 = fminf(best_d2, d2);
 }
 
 __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
@@ -272,6 +302,88 @@ knn_tc_kernel(const float* __restrict__ f0, int n0, const float* __restrict__ f1
       }
       __syncwarp();
     }
+  } else if (PASS == 3) {
+    // ================================ single sweep: thread = (F0 row, column half) ========
+    // One pass over the products.  The candidate bound follows the RUNNING row minimum of this thread's columns
+    // (any upper bound of the final minimum keeps the candidate set a superset, see the header): columns within the
+    // bound are buffered in shared memory (column, estimate) and evaluated exactly after the sweep against the
+    // final - tightest - bound; a full buffer evaluates the newcomer on the spot.
+    const int lane_grp = warp & 3;
+    const int half = (warp - kLoadWarps - 1) >> 2;
+    const int gi = row0 + lane_grp * 32 + lane;
+    const bool valid = gi < n0;
+    const int etid = (warp - kLoadWarps - 1) * 32 + lane;                  // 0 .. kEpiThreads-1
+    int* cand_j = reinterpret_cast<int*>(b_stage0 + 2 * (size_t)kStageBytes) + etid;       // [slot][thread]
+    float* cand_g = reinterpret_cast<float*>(cand_j - etid + kCandCap * kEpiThreads) + etid;
+    const float ninf = -__int_as_float(0x7f800000), pinf = __int_as_float(0x7f800000);
+    const float na2_i = valid ? na2[gi] : 0.f;
+    const float e4 = valid ? 4.f * knn_error_bound(sqrtf(na2_i), sqrtf(__uint_as_float(*nb2_max_bits)), kFine) : 0.f;
+    float rmin = pinf, th_exact = pinf;
+    float best_s = pinf, best_d2 = pinf;
+    int best_j = 0x7fffffff, cnt = 0;
+    // bound in the epilogue's units (0.5 |b|^2 - a.b), from the running minimum: thr kernel's formula
+    auto bound = [&](float m) { return 0.5f * (fmaxf(fmaf(2.f, m, na2_i), 0.f) + e4 - na2_i); };
+    auto take = [&](int j, float g) {
+      if (cnt < kCandCap) {
+        cand_j[cnt * kEpiThreads] = j;
+        cand_g[cnt * kEpiThreads] = g;
+        ++cnt;
+      } else {
+        knn_exact_candidate_unordered<C>(f0, f1, gi, j, best_s, best_d2, best_j);
+        th_exact = fminf(th_exact, 0.5f * (best_d2 + e4 - na2_i));
+      }
+    };
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int j0 = col_begin + it * kColsB + half * 128;
+      mbar_wait(smem_u32(&sh.acc_full[s]), ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)s * kColsB + half * 128 + ((uint32_t)(lane_grp * 32) << 16);
+      const float* hb = sh.nb[s] + half * 128;
+      uint32_t va[32], vb[32];
+      tc_ld32_issue(taddr, va);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        tc_ld_wait();
+        uint32_t(&cur)[32] = (cc & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (cc & 1) ? va : vb;
+        if (cc < 3) tc_ld32_issue(taddr + (cc + 1) * 32, nxt);
+        const int jc = j0 + cc * 32;
+        if (jc < col_end) {
+          const int nq = min(32, col_end - jc);
+          float cmin = pinf;
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            cmin = fminf(cmin, q < nq ? hb[cc * 32 + q] - __uint_as_float(cur[q]) : pinf);
+          rmin = fminf(rmin, cmin);
+          float th = valid ? fminf(th_exact, bound(rmin)) : ninf;
+          if (cmin <= th) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const float g = hb[cc * 32 + q] - __uint_as_float(cur[q]);
+              if (q < nq && g <= th) {
+                take(jc + q, g);
+                th = fminf(th, th_exact);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh.acc_empty[s]));
+    }
+    if (valid) {
+      float th = fminf(th_exact, bound(rmin));
+      for (int k = 0; k < cnt; ++k) {
+        if (cand_g[k * kEpiThreads] <= th) {
+          knn_exact_candidate_unordered<C>(f0, f1, gi, cand_j[k * kEpiThreads], best_s, best_d2, best_j);
+          th = fminf(th, 0.5f * (best_d2 + e4 - na2_i));
+        }
+      }
+      if (best_j != 0x7fffffff)
+        atomicMin(packed + gi, ((unsigned long long)__float_as_uint(best_s) << 32) | (unsigned)best_j);
+    }
   } else {
     // ================================ epilogue: thread = (F0 row, column half) ============
     const int lane_grp = warp & 3;
@@ -367,6 +479,26 @@ __global__ void knn_tc_unpack_kernel(const unsigned long long* __restrict__ pack
   if (dist != nullptr) dist[i] = __uint_as_float((unsigned)(p >> 32));
 }
 
+// single sweep (DGR_KNN_SWEEPS=1): no row-minimum pass, no threshold kernel
+template <int C>
+int32_t launch_knn_tc_single(const float* f0, int64_t n0, const float* f1, int64_t n1, float* na2, float* nb2,
+                             unsigned* max_bits, unsigned long long* packed, cudaStream_t st) {
+  constexpr int kChunks = C / 32;
+  const size_t smem = sizeof(KnnShared) + 1024 + (size_t)kChunks * kATile + 2 * (size_t)kChunks * kBTile + kCandBytes;
+  DGR_ENSURE_SMEM((knn_tc_kernel<C, 3, false>), smem);
+  const int row_tiles = (int)((n0 + kRowsA - 1) / kRowsA);
+  const int col_tiles = (int)((n1 + kColsB - 1) / kColsB);
+  int splits = (148 * 4 + row_tiles - 1) / row_tiles;
+  if (splits > col_tiles) splits = col_tiles;
+  if (splits < 1) splits = 1;
+  const int cols_per_split = ((col_tiles + splits - 1) / splits) * kColsB;
+  splits = (int)((n1 + cols_per_split - 1) / cols_per_split);
+  dim3 grid(row_tiles, splits);
+  knn_tc_kernel<C, 3, false><<<grid, kThreadsK, smem, st>>>(f0, (int)n0, f1, (int)n1, na2, nb2, cols_per_split,
+                                                            nullptr, nullptr, packed, max_bits);
+  return DGR_OK;
+}
+
 template <int C, bool kFine>
 int32_t launch_knn_tc(const float* f0, int64_t n0, const float* f1, int64_t n1, float* na2, float* nb2,
                       unsigned* rowmin, float* thr, unsigned* max_bits, unsigned long long* packed,
@@ -423,6 +555,17 @@ int32_t dgr_knn_top1_tc(const float* f0, int64_t n0, const float* f1, int64_t n1
   // default: single TF32 product per term.  DGR_KNN_FINE=1 (c = 32 only): 3xTF32 products, a ~150x narrower
   // candidate band, measured slower (the hi + lo tiles double the operand staging)
   static const bool coarse = getenv("DGR_KNN_FINE") == nullptr;        // A/B switch: 3xTF32 pre-filter (slower)
+  // DGR_KNN_SWEEPS=1: the single-sweep variant (running bound + candidate buffer)
+  static const bool single = getenv("DGR_KNN_SWEEPS") != nullptr && atoi(getenv("DGR_KNN_SWEEPS")) == 1;
+  if (single) {
+    int32_t rc1 = (c == 32) ? launch_knn_tc_single<32>(f0, n0, f1, n1, na2, nb2, max_bits, packed, st)
+                            : launch_knn_tc_single<64>(f0, n0, f1, n1, na2, nb2, max_bits, packed, st);
+    if (rc1 != DGR_OK) return rc1;
+    knn_tc_unpack_kernel<<<dgr_blocks(n0, 256), 256, 0, st>>>(packed, n0, idx, dist);
+    dgr_note_launches(5);
+    DGR_LAUNCH_CHECK();
+    return DGR_OK;
+  }
   int32_t rc = (c == 32) ? (coarse ? launch_knn_tc<32, false>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st)
                                    : launch_knn_tc<32, true>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st))
                          : launch_knn_tc<64, false>(f0, n0, f1, n1, na2, nb2, rowmin, thr, max_bits, packed, st);
