@@ -1,6 +1,7 @@
 """The pair-list evaluation driver (evaluate.py: what scripts/test_3dmatch.py / test_kitti.py do
 around register()) on CPU: metric, 3DMatch tree and pair-list parsing, file-backed pairs through
 the sharded loop at world size 1 and 2 (gloo), summary numbers."""
+import datetime
 import math
 import os
 import socket
@@ -103,7 +104,7 @@ def test_pair_list_formats(tmp_path):
 
 def _worker(rank, world, port, root):
   os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
-  dist.init_process_group('gloo', rank=rank, world_size=world)
+  dist.init_process_group('gloo', rank=rank, world_size=world, timeout=datetime.timedelta(seconds=90))
   res = ev.evaluate(_CentroidRegistrar(), ev.threedmatch_pairs(root), 0.3, 15)
   torch.save(res['stats'], os.path.join(root, f'stats{rank}.pt'))
   dist.destroy_process_group()
@@ -112,11 +113,17 @@ def _worker(rank, world, port, root):
 def test_two_ranks_agree_with_one(tmp_path):
   _tree(str(tmp_path))
   one = ev.evaluate(_CentroidRegistrar(), ev.threedmatch_pairs(str(tmp_path)), 0.3, 15)['stats']
-  s = socket.socket()
-  s.bind(('127.0.0.1', 0))
-  port = s.getsockname()[1]
-  s.close()
-  mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  for attempt in range(3):                      # a lost rendezvous (port taken in between) is retried, not waited on
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    try:
+      mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+      break
+    except Exception:
+      if attempt == 2:
+        raise
   r0, r1 = torch.load(tmp_path / 'stats0.pt', weights_only=False), torch.load(tmp_path / 'stats1.pt', weights_only=False)
   assert np.array_equal(r0[:, [0, 4]], one[:, [0, 4]]) and np.array_equal(r0[:, :3], r1[:, :3])
   np.testing.assert_allclose(r0[:, 1:3], one[:, 1:3], atol=1e-9)

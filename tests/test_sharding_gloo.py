@@ -1,5 +1,6 @@
 """World-size-2 test of the pair-sharding host logic on CPU (gloo): ownership, result
 packing and the all-gather return every pair's result, in order, on every rank."""
+import datetime
 import os
 import socket
 
@@ -28,7 +29,7 @@ def _pairs(n):
 
 def _worker(rank, world, port, n_pairs, out_dir):
   os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
-  dist.init_process_group('gloo', rank=rank, world_size=world)
+  dist.init_process_group('gloo', rank=rank, world_size=world, timeout=datetime.timedelta(seconds=90))
   res = sharding.register_pairs(_FakeDgr(), _pairs(n_pairs))
   torch.save(res, os.path.join(out_dir, f'r{rank}.pt'))
   dist.destroy_process_group()
@@ -40,6 +41,18 @@ def _free_port():
   p = s.getsockname()[1]
   s.close()
   return p
+
+
+def _spawn(fn, world, *args):
+  """mp.spawn on a fresh port; a lost rendezvous (the port was taken between _free_port() and the bind) times out
+  in the workers and is retried instead of hanging the suite."""
+  for attempt in range(3):
+    try:
+      mp.spawn(fn, args=(world, _free_port(), *args), nprocs=world, join=True)
+      return
+    except Exception:
+      if attempt == 2:
+        raise
 
 
 def test_shard_indices_cover_everything_once():
@@ -55,7 +68,7 @@ def test_single_process_path():
 
 def test_two_rank_gloo_all_gather(tmp_path):
   n_pairs, world = 7, 2
-  mp.spawn(_worker, args=(world, _free_port(), n_pairs, str(tmp_path)), nprocs=world, join=True)
+  _spawn(_worker, world, n_pairs, str(tmp_path))
   r0, r1 = torch.load(tmp_path / 'r0.pt'), torch.load(tmp_path / 'r1.pt')
   assert torch.equal(r0, r1) and r0.shape == (n_pairs, 20)
   for i in range(n_pairs):
@@ -89,7 +102,7 @@ class _FakeBatchDgr(_FakeDgr):
 
 def _worker_batch(rank, world, port, n_pairs, out_dir):
   os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
-  dist.init_process_group('gloo', rank=rank, world_size=world)
+  dist.init_process_group('gloo', rank=rank, world_size=world, timeout=datetime.timedelta(seconds=90))
   res = sharding.register_pairs(_FakeBatchDgr(), _pairs(n_pairs), inflight=3)
   torch.save(res, os.path.join(out_dir, f'b{rank}.pt'))
   dist.destroy_process_group()
@@ -97,7 +110,7 @@ def _worker_batch(rank, world, port, n_pairs, out_dir):
 
 def test_batch_api_two_ranks_keep_pair_order(tmp_path):
   n_pairs, world = 11, 2
-  mp.spawn(_worker_batch, args=(world, _free_port(), n_pairs, str(tmp_path)), nprocs=world, join=True)
+  _spawn(_worker_batch, world, n_pairs, str(tmp_path))
   r0, r1 = torch.load(tmp_path / 'b0.pt'), torch.load(tmp_path / 'b1.pt')
   assert torch.equal(r0[:, :19], r1[:, :19]) and r0.shape == (n_pairs, 20)
   for i in range(n_pairs):
