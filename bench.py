@@ -59,7 +59,7 @@ def base_config(n_gpus):
   (voxel counts seen, sample notes) goes into other keys of the line."""
   return {'workload': WORKLOAD, 'n_raw_points_per_scan': N_RAW, 'voxel_size': VOXEL, 'feat_dim': 32,
           'fcgf_model': 'ResUNetBN2C(D=3,conv1_k=7)', 'inlier_model': 'ResUNetBN2C(D=6,conv1_k=3)',
-          'conv_arithmetic': 'tcgen05 3xTF32 (fp32-accurate) + fp32 FFMA for conv1',
+          'conv_arithmetic': 'tcgen05 split products, fp32 accumulate: 3xFP16 hi/lo on the wide layers, 3xTF32 elsewhere (both fp32-accurate: features within 5e-5 of the fp32 oracle at full size); fp32 adds for conv1',
           'parallelism': f'pair-sharded dp{n_gpus}', 'pairs_per_step_per_gpu': 1,
           'excluded_on_both_arms': 'ICP fine-tune and RANSAC safeguard (both built; the benchmarked unit is SURVEY 8(d)\'s: through the SE(3) refinement, and the benchmark pairs take the Procrustes branch)',
           'l2_policy': 'inputs larger than L2: every step streams the 944 MB inlier-net weights '
